@@ -1,0 +1,842 @@
+// Forward kernels of the NodeEdgeNet hot path (reference: models/graph.py:10-55,122-141,251-396) and the
+// C-ABI entry points declared in include/moldiff_b200.h.
+//
+// Kernel schedule for one network forward (L blocks):
+//   node_init, edge_init                       embedders + time features         model.py:210-213
+//   node_kernel(pre 0)                         per-node hoisted projections for block 0
+//   for i in 0..L-1:
+//     edge_kernel_b(i)   RBF, edge_embs[i], NodeBlock edge path -> AGG, BondFFN L/R -> SL/SR
+//     node_kernel(mid i, pre i+1 | decode)     NodeBlock node path, h_node residual, PosUpdate node MLPs,
+//                                              hoisted projections for block i+1
+//     edge_kernel_d(i)   EdgeBlock tail -> h_edge, PosUpdate edge path -> pos
+//   edge_decode                                 edge decoder on h_edge[p] + h_edge[p + E/2]
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/moldiff_b200.h"
+#include "tile_engine.cuh"
+
+using namespace mdb;
+
+namespace {
+
+constexpr int D = MDB_NODE_DIM;   // 256
+constexpr int C = MDB_EDGE_DIM;   // 64
+constexpr int G = MDB_NUM_RBF;    // 16
+
+struct BlkOff { int o[MDB_NUM_BLOCK_SLOTS]; };
+struct HeadOff { int o[MDB_NUM_HEAD_SLOTS]; };
+
+// Per-node tables produced by node_kernel and gathered by the edge kernels (workspace carve-up).
+struct Tables {
+  float *x, *agg, *hn, *gx, *cen;       // [N][256]
+  float *nll, *nlr;                     // [N][128]   bond_ffn_{left,right}.node_linear(h_node)
+  float *gnl, *gnr;                     // [N][32]    bond_ffn gate first layer, node + time + bias part
+  float *fl, *fr, *lf, *rf, *dect;      // [N][64]
+  float *slsr;                          // [2 parities][2 (SL,SR)][N][64]
+  float *pos0, *pos1;                   // [N][3]
+  float *tn;                            // [N]
+  float *hedge, *ebuf;                  // [E][64] sorted order
+  float *te;                            // [E]
+};
+
+#define W_(slot) (blob + off.o[MDB_S_##slot])
+#define H_(slot) (blob + hoff.o[MDB_H_##slot])
+
+// ------------------------------------------------------------------------------------------------
+// init kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float smear(float v, float lo, float hi, float offset, float coeff) {
+  const float d = fminf(fmaxf(v, lo), hi) - offset;
+  return expf(coeff * (d * d));   // coeff * pow(d, 2): same rounding order as common.py:237
+}
+
+// kind 1/2: x[n] = [node_embedder(h_node_pert[n]) ; time_emb(t[batch[n]])], tn[n] = t/T.  kind 0: copy.
+__global__ void node_init_kernel(int kind, int n_nodes, int kn, int time_dim, float T,
+                                 const float* __restrict__ blob, HeadOff hoff,
+                                 const float* __restrict__ h_in, const int64_t* __restrict__ batch,
+                                 const int64_t* __restrict__ t, const float* __restrict__ node_time,
+                                 float* __restrict__ x, float* __restrict__ tn) {
+  const int n = blockIdx.x;
+  const int c = threadIdx.x;
+  if (kind == 0) {
+    x[(size_t)n * D + c] = h_in[(size_t)n * D + c];
+    if (c == 0) tn[n] = node_time[n];
+    return;
+  }
+  const float tt = (float)t[batch[n]];
+  const int de = D - time_dim;
+  float v;
+  if (c < de) {
+    const float* w = H_(NODE_EMB_W);
+    v = 0.f;
+    for (int k = 0; k < kn; ++k) v = fmaf(h_in[(size_t)n * kn + k], w[k * de + c], v);
+  } else {
+    const int j = c - de;
+    v = smear(tt, 0.f, T, H_(TIME_OFFSET)[j], H_(TIME_COEFF)[j]);
+  }
+  x[(size_t)n * D + c] = v;
+  if (c == 0) tn[n] = tt / T;
+}
+
+// Sorted edge q (orig id p = perm[q]).  kind 1: [edge_embedder(h_edge_pert[p]) ; time_emb]; kind 2:
+// [edge_embedder(cat(h_node[l], h_node[r])) ; time_emb] (bond_predictor.py:135-140); kind 0: gather.
+__global__ void edge_init_kernel(int kind, int n_edges, int kn, int ke, int time_dim, float T,
+                                 const float* __restrict__ blob, HeadOff hoff,
+                                 const float* __restrict__ h_edge_in, const float* __restrict__ h_node_in,
+                                 const int64_t* __restrict__ batch_edge, const int64_t* __restrict__ t,
+                                 const float* __restrict__ edge_time,
+                                 const int* __restrict__ left, const int* __restrict__ right,
+                                 const int* __restrict__ perm,
+                                 float* __restrict__ hedge, float* __restrict__ te) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int c = threadIdx.x & 63;
+  if (q >= n_edges) return;
+  const int p = perm[q];
+  if (kind == 0) {
+    hedge[(size_t)q * C + c] = h_edge_in[(size_t)p * C + c];
+    if (c == 0) te[q] = edge_time[p];
+    return;
+  }
+  const float tt = (float)t[batch_edge[p]];
+  const int de = C - time_dim;
+  float v;
+  if (c < de) {
+    const float* w = H_(EDGE_EMB_W);
+    v = 0.f;
+    if (kind == 1) {
+      for (int k = 0; k < ke; ++k) v = fmaf(h_edge_in[(size_t)p * ke + k], w[k * de + c], v);
+    } else {
+      const int l = left[q], r = right[q];
+      for (int k = 0; k < kn; ++k) v = fmaf(h_node_in[(size_t)l * kn + k], w[k * de + c], v);
+      for (int k = 0; k < kn; ++k) v = fmaf(h_node_in[(size_t)r * kn + k], w[(kn + k) * de + c], v);
+    }
+  } else {
+    const int j = c - de;
+    v = smear(tt, 0.f, T, H_(TIME_OFFSET)[j], H_(TIME_COEFF)[j]);
+  }
+  hedge[(size_t)q * C + c] = v;
+  if (c == 0) te[q] = tt / T;
+}
+
+// ------------------------------------------------------------------------------------------------
+// node kernel: one 64-node tile per CTA
+// ------------------------------------------------------------------------------------------------
+struct NodeArgs {
+  const float* blob;
+  BlkOff mid, pre;      // offsets of block i (mid) and block i+1 (pre)
+  HeadOff head;
+  Tables tb;
+  int n_nodes;
+  int do_mid, do_pre, do_dec;   // phases
+  int update_pos;
+  int kind, kn;
+  int par_next;                 // parity of the SL/SR buffer to clear for the `pre` block
+  const float* pos_cur;
+  float* pos_nxt;
+  float* pred_node;             // kind 1 decode target [N][kn]
+};
+
+template <int N>
+__device__ __forceinline__ void store_table(const float (&acc)[8][N / 32], float* __restrict__ table, int row0,
+                                            int n_rows, int warp, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = row0 + warp * 8 + i;
+    if (n < n_rows) store_cols<N>(acc[i], table + (size_t)n * N, lane);
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) node_kernel(const NodeArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* X = smem;                 // [64][256]
+  float* A = X + TM * D;           // [64][256]
+  float* Ws = A + TM * D;          // 2*WCHUNK
+  float* tns = Ws + 2 * WCHUNK;    // [64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * TM;
+  const float* blob = a.blob;
+  const Tables& tb = a.tb;
+
+  // load x tile (+ node time)
+  for (int i = tid; i < TM * D / 4; i += NTHREADS) {
+    const int r = i / (D / 4), c4 = i % (D / 4);
+    const int n = row0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < a.n_nodes) v = reinterpret_cast<const float4*>(tb.x + (size_t)n * D)[c4];
+    reinterpret_cast<float4*>(X + r * D)[c4] = v;
+  }
+  if (tid < TM) tns[tid] = (row0 + tid < a.n_nodes) ? tb.tn[row0 + tid] : 0.f;
+  __syncthreads();
+
+  if (a.do_mid) {
+    const BlkOff& off = a.mid;
+    {  // out = LN(centroid_lin(x) + aggr) -> ReLU                                   graph.py:51-54
+      float acc[8][8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = row0 + warp * 8 + i;
+        if (n < a.n_nodes) {
+          float u[8], v[8];
+          load_cols<D>(u, tb.cen + (size_t)n * D, lane);
+          load_cols<D>(v, tb.agg + (size_t)n * D, lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[i][j] = u[j] + v[j]; v[j] = 0.f; }
+          store_cols<D>(v, tb.agg + (size_t)n * D, lane);   // re-arm the accumulator for the next block
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        }
+      }
+      layernorm_rows<D, true>(acc, W_(NB_LN_G), W_(NB_LN_BE), lane);
+      store_smem<D>(acc, A, D, warp, lane);
+    }
+    {  // h_node = h_node + out_transform(.)                                        graph.py:54,363
+      float acc[8][8];
+      tile_gemm<D, D>(acc, A, D, W_(NB_OUT_W), Ws);
+      add_rowvec<D>(acc, W_(NB_OUT_B), lane);
+      combine_smem<D, false>(acc, X, D, warp, lane);
+      store_smem<D>(acc, X, D, warp, lane);
+      store_table<D>(acc, tb.x, row0, a.n_nodes, warp, lane);
+    }
+    if (a.update_pos) {  // PosUpdate node-side MLPs on the NEW h_node             graph.py:387-388
+#pragma unroll 1
+      for (int side = 0; side < 2; ++side) {
+        float acc[8][2];
+        tile_gemm<D, C>(acc, X, D, side ? W_(PU_RL1_W) : W_(PU_LL1_W), Ws);
+        add_rowvec<C>(acc, side ? W_(PU_RL1_B) : W_(PU_LL1_B), lane);
+        layernorm_rows<C, true>(acc, side ? W_(PU_RL1_G) : W_(PU_LL1_G), side ? W_(PU_RL1_BE) : W_(PU_LL1_BE), lane);
+        store_smem<C>(acc, A, C, warp, lane);
+        tile_gemm<C, C>(acc, A, C, side ? W_(PU_RL2_W) : W_(PU_LL2_W), Ws);
+        add_rowvec<C>(acc, side ? W_(PU_RL2_B) : W_(PU_LL2_B), lane);
+        store_table<C>(acc, side ? tb.rf : tb.lf, row0, a.n_nodes, warp, lane);
+      }
+      // pos_nxt starts as pos_cur; edge_kernel_d accumulates the forces into it     graph.py:366
+      for (int i = tid; i < TM * 3; i += NTHREADS) {
+        const int n = row0 + i / 3;
+        if (n < a.n_nodes) a.pos_nxt[(size_t)row0 * 3 + i] = a.pos_cur[(size_t)row0 * 3 + i];
+      }
+    }
+  }
+
+  if (a.do_pre) {
+    const BlkOff& off = a.pre;
+    {  // node_net(x)                                                                graph.py:39
+      float acc[8][8];
+      tile_gemm<D, D>(acc, X, D, W_(NB_NN1_W), Ws);
+      add_rowvec<D>(acc, W_(NB_NN1_B), lane);
+      layernorm_rows<D, true>(acc, W_(NB_NN1_G), W_(NB_NN1_BE), lane);
+      store_smem<D>(acc, A, D, warp, lane);
+      tile_gemm<D, D>(acc, A, D, W_(NB_NN2_W), Ws);
+      add_rowvec<D>(acc, W_(NB_NN2_B), lane);
+      store_table<D>(acc, tb.hn, row0, a.n_nodes, warp, lane);
+    }
+    {  // node + time + bias part of gate.net.0 (hoisted from the per-edge cat)      graph.py:46
+      float acc[8][8];
+      tile_gemm<D, D>(acc, X, D, W_(NB_GX_W), Ws);
+      add_rowvec<D>(acc, W_(NB_G1_B), lane);
+      add_scaled_rowvec<D>(acc, W_(NB_GT_W), tns + warp * 8, lane);
+      store_table<D>(acc, tb.gx, row0, a.n_nodes, warp, lane);
+    }
+    {  // centroid_lin(x)                                                            graph.py:51
+      float acc[8][8];
+      tile_gemm<D, D>(acc, X, D, W_(NB_CEN_W), Ws);
+      add_rowvec<D>(acc, W_(NB_CEN_B), lane);
+      store_table<D>(acc, tb.cen, row0, a.n_nodes, warp, lane);
+    }
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {   // EdgeBlock hoists                     graph.py:135,139,288-289
+      {
+        float acc[8][4];
+        tile_gemm<D, 128>(acc, X, D, side ? W_(ER_NL_W) : W_(EL_NL_W), Ws);
+        store_table<128>(acc, side ? tb.nlr : tb.nll, row0, a.n_nodes, warp, lane);
+      }
+      {
+        float acc[8][1];
+        tile_gemm<D, 32>(acc, X, D, side ? W_(ER_GN_W) : W_(EL_GN_W), Ws);
+        add_rowvec<32>(acc, side ? W_(ER_G1_B) : W_(EL_G1_B), lane);
+        add_scaled_rowvec<32>(acc, side ? W_(ER_GT_W) : W_(EL_GT_W), tns + warp * 8, lane);
+        store_table<32>(acc, side ? tb.gnr : tb.gnl, row0, a.n_nodes, warp, lane);
+      }
+      {
+        float acc[8][2];
+        tile_gemm<D, C>(acc, X, D, side ? W_(EB_NFR_W) : W_(EB_NFL_W), Ws);
+        add_rowvec<C>(acc, side ? W_(EB_NFR_B) : W_(EB_NFL_B), lane);
+        store_table<C>(acc, side ? tb.fr : tb.fl, row0, a.n_nodes, warp, lane);
+      }
+    }
+    // clear the SL/SR accumulators the next edge_kernel_b will add into
+    float* sl = tb.slsr + (size_t)a.par_next * 2 * a.n_nodes * C;
+    for (int i = tid; i < TM * C; i += NTHREADS) {
+      const int n = row0 + i / C;
+      if (n < a.n_nodes) {
+        sl[(size_t)row0 * C + i] = 0.f;
+        sl[(size_t)a.n_nodes * C + (size_t)row0 * C + i] = 0.f;
+      }
+    }
+  }
+
+  if (a.do_dec) {
+    const HeadOff& hoff = a.head;
+    if (a.kind == 1) {  // node_decoder MLP(256 -> 256 -> Kn)                         model.py:226
+      float acc[8][8];
+      tile_gemm<D, D>(acc, X, D, H_(NDEC1_W), Ws);
+      add_rowvec<D>(acc, H_(NDEC1_B), lane);
+      layernorm_rows<D, true>(acc, H_(NDEC1_G), H_(NDEC1_BE), lane);
+      store_smem<D>(acc, A, D, warp, lane);
+      float o[8][1];
+      tile_gemm<D, 32>(o, A, D, H_(NDEC2_W), Ws);
+      add_rowvec<32>(o, H_(NDEC2_B), lane);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = row0 + warp * 8 + i;
+        if (n < a.n_nodes && lane < a.kn) a.pred_node[(size_t)n * a.kn + lane] = o[i][0];
+      }
+    } else if (a.kind == 2) {  // node half of edge_decoder.net.0                     bond_predictor.py:155-160
+      float acc[8][2];
+      tile_gemm<D, C>(acc, X, D, H_(EDEC1N_W), Ws);
+      store_table<C>(acc, tb.dect, row0, a.n_nodes, warp, lane);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge kernel B: RBF + edge_embs + NodeBlock edge path + BondFFN left/right     (64 sorted edges / CTA)
+// ------------------------------------------------------------------------------------------------
+struct EdgeArgs {
+  const float* blob;
+  BlkOff off;
+  HeadOff head;
+  Tables tb;
+  const int *left, *right;
+  int n_nodes, n_edges;
+  int update_pos;
+  int par;                    // SL/SR parity of this block
+  float rbf_lo, rbf_hi;
+  const float* pos_cur;
+  float* pos_nxt;
+};
+
+__device__ __forceinline__ void load_edge_meta(const EdgeArgs& a, int q0, int* ls, int* rs, float* tes,
+                                               float* rel /* [4][64]: x,y,z,d */) {
+  const int tid = threadIdx.x;
+  if (tid < TM) {
+    const int q = q0 + tid;
+    int l = -1, r = -1;
+    float t = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, d = 1.f;
+    if (q < a.n_edges) {
+      l = a.left[q]; r = a.right[q]; t = a.tb.te[q];
+      dx = a.pos_cur[l * 3 + 0] - a.pos_cur[r * 3 + 0];
+      dy = a.pos_cur[l * 3 + 1] - a.pos_cur[r * 3 + 1];
+      dz = a.pos_cur[l * 3 + 2] - a.pos_cur[r * 3 + 2];
+      d = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    ls[tid] = l; rs[tid] = r; tes[tid] = t;
+    rel[tid] = dx; rel[TM + tid] = dy; rel[2 * TM + tid] = dz; rel[3 * TM + tid] = d;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_b(const EdgeArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Es = smem;                  // [64][64]   e = edge_embs(cat(h_edge, rbf))
+  float* A = Es + TM * C;            // [64][256]
+  float* Bf = A + TM * D;            // [64][256]
+  float* Ws = Bf + TM * D;           // 2*WCHUNK
+  float* tes = Ws + 2 * WCHUNK;      // [64]
+  float* rel = tes + TM;             // [4][64]
+  int* ls = reinterpret_cast<int*>(rel + 4 * TM);
+  int* rs = ls + TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.x * TM;
+  const float* blob = a.blob;
+  const BlkOff& off = a.off;
+  const Tables& tb = a.tb;
+
+  load_edge_meta(a, q0, ls, rs, tes, rel);
+  // IN = [h_edge ; rbf(d)]  as A[64][80]
+  constexpr int KI = C + G;
+  for (int i = tid; i < TM * C / 4; i += NTHREADS) {
+    const int r = i / (C / 4), c4 = i % (C / 4);
+    const int q = q0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < a.n_edges) v = reinterpret_cast<const float4*>(tb.hedge + (size_t)q * C)[c4];
+    *reinterpret_cast<float4*>(A + r * KI + c4 * 4) = v;
+  }
+  __syncthreads();
+  {
+    const HeadOff& hoff = a.head;
+    const float* ro = H_(RBF_OFFSET);
+    const float* rc = H_(RBF_COEFF);
+    for (int i = tid; i < TM * G; i += NTHREADS) {
+      const int r = i / G, k = i % G;
+      A[r * KI + C + k] = smear(rel[3 * TM + r], a.rbf_lo, a.rbf_hi, ro[k], rc[k]);
+    }
+  }
+  __syncthreads();
+  const int* lw = ls + warp * 8;
+  const int* rw = rs + warp * 8;
+  {  // e = edge_embs[i](cat)                                                        graph.py:354-357
+    float acc[8][2];
+    tile_gemm<KI, C>(acc, A, KI, W_(EE_W), Ws);
+    add_rowvec<C>(acc, W_(EE_B), lane);
+    store_smem<C>(acc, Es, C, warp, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + warp * 8 + i;
+      if (q < a.n_edges) store_cols<C>(acc[i], tb.ebuf + (size_t)q * C, lane);
+    }
+  }
+  // ---- NodeBlock edge path                                                       graph.py:42-50
+  {
+    float acc[8][8];
+    tile_gemm<C, D>(acc, Es, C, W_(NB_EN1_W), Ws);           // edge_net.net.0
+    add_rowvec<D>(acc, W_(NB_EN1_B), lane);
+    layernorm_rows<D, true>(acc, W_(NB_EN1_G), W_(NB_EN1_BE), lane);
+    store_smem<D>(acc, A, D, warp, lane);
+    tile_gemm<D, D>(acc, A, D, W_(NB_EN2_W), Ws);            // edge_net.net.3
+    add_rowvec<D>(acc, W_(NB_EN2_B), lane);
+    gather_rows<D, true>(acc, tb.hn, rw, lane);              // * node_net(x)[col]
+    store_smem<D>(acc, Bf, D, warp, lane);
+    tile_gemm<C, D>(acc, Es, C, W_(NB_GE_W), Ws);            // gate.net.0, edge columns
+    gather_rows<D, false>(acc, tb.gx, rw, lane);             //   + hoisted node/time/bias part
+    layernorm_rows<D, true>(acc, W_(NB_G1_G), W_(NB_G1_BE), lane);
+    store_smem<D>(acc, A, D, warp, lane);
+    tile_gemm<D, D>(acc, A, D, W_(NB_G2_W), Ws);             // gate.net.3
+    add_rowvec<D>(acc, W_(NB_G2_B), lane);
+    sigmoid_rows<D>(acc);
+    store_smem<D>(acc, A, D, warp, lane);
+    tile_gemm<D, D>(acc, Bf, D, W_(NB_MSG_W), Ws);           // msg_net
+    add_rowvec<D>(acc, W_(NB_MSG_B), lane);
+    combine_smem<D, true>(acc, A, D, warp, lane);
+    scatter_add_rows<D, true>(acc, tb.agg, lw, lane);        // scatter_sum over row (= left)
+  }
+  // ---- EdgeBlock: bond_ffn_left (node = left, scattered to right) and _right      graph.py:278-284
+  float* sl = tb.slsr + (size_t)a.par * 2 * a.n_nodes * C;
+  float* sr = sl + (size_t)a.n_nodes * C;
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const int* nw = side ? rw : lw;   // node feeding the FFN
+    float inter[8][2];
+    {
+      float acc[8][4];
+      tile_gemm<C, 128>(acc, Es, C, side ? W_(ER_BL_W) : W_(EL_BL_W), Ws);      // bond_linear
+      gather_rows<128, true>(acc, side ? tb.nlr : tb.nll, nw, lane);            // * node_linear(h_node)[.]
+      store_smem<128>(acc, A, 128, warp, lane);
+      tile_gemm<128, 128>(acc, A, 128, side ? W_(ER_I1_W) : W_(EL_I1_W), Ws);   // inter_module
+      add_rowvec<128>(acc, side ? W_(ER_I1_B) : W_(EL_I1_B), lane);
+      layernorm_rows<128, true>(acc, side ? W_(ER_I1_G) : W_(EL_I1_G), side ? W_(ER_I1_BE) : W_(EL_I1_BE), lane);
+      store_smem<128>(acc, A, 128, warp, lane);
+      tile_gemm<128, C>(inter, A, 128, side ? W_(ER_I2_W) : W_(EL_I2_W), Ws);
+      add_rowvec<C>(inter, side ? W_(ER_I2_B) : W_(EL_I2_B), lane);
+    }
+    {
+      float g1[8][1];
+      tile_gemm<C, 32>(g1, Es, C, side ? W_(ER_GB_W) : W_(EL_GB_W), Ws);        // gate.net.0 bond columns
+      gather_rows<32, false>(g1, side ? tb.gnr : tb.gnl, nw, lane);
+      layernorm_rows<32, true>(g1, side ? W_(ER_G1_G) : W_(EL_G1_G), side ? W_(ER_G1_BE) : W_(EL_G1_BE), lane);
+      store_smem<32>(g1, Bf, 32, warp, lane);
+      float g2[8][2];
+      tile_gemm<32, C>(g2, Bf, 32, side ? W_(ER_G2_W) : W_(EL_G2_W), Ws);
+      add_rowvec<C>(g2, side ? W_(ER_G2_B) : W_(EL_G2_B), lane);
+      sigmoid_rows<C>(g2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { inter[i][0] *= g2[i][0]; inter[i][1] *= g2[i][1]; }
+    }
+    if (side == 0) scatter_add_rows<C, false>(inter, sl, rw, lane);   // scatter over right_node
+    else           scatter_add_rows<C, true>(inter, sr, lw, lane);    // scatter over left_node
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge kernel D: EdgeBlock tail (-> new h_edge) + PosUpdate edge path (-> pos)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_d(const EdgeArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Es = smem;                  // [64][64]  e
+  float* E2 = Es + TM * C;           // [64][64]  new h_edge
+  float* P = E2 + TM * C;            // [64][64]  left_feat * right_feat
+  float* A = P + TM * C;             // [64][256]
+  float* Ws = A + TM * D;
+  float* tes = Ws + 2 * WCHUNK;
+  float* rel = tes + TM;
+  int* ls = reinterpret_cast<int*>(rel + 4 * TM);
+  int* rs = ls + TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.x * TM;
+  const float* blob = a.blob;
+  const BlkOff& off = a.off;
+  const Tables& tb = a.tb;
+
+  load_edge_meta(a, q0, ls, rs, tes, rel);
+  for (int i = tid; i < TM * C / 4; i += NTHREADS) {
+    const int r = i / (C / 4), c4 = i % (C / 4);
+    const int q = q0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < a.n_edges) v = reinterpret_cast<const float4*>(tb.ebuf + (size_t)q * C)[c4];
+    reinterpret_cast<float4*>(Es + r * C)[c4] = v;
+  }
+  __syncthreads();
+  const int* lw = ls + warp * 8;
+  const int* rw = rs + warp * 8;
+  const float* sl = tb.slsr + (size_t)a.par * 2 * a.n_nodes * C;
+  const float* sr = sl + (size_t)a.n_nodes * C;
+  {  // graph.py:286-294
+    float acc[8][2];
+    tile_gemm<C, C>(acc, Es, C, W_(EB_SELF_W), Ws);
+    add_rowvec<C>(acc, W_(EB_SELF_B), lane);
+    gather_rows<C, false>(acc, sl, lw, lane);       // scatter_sum(msg_left, right)[left]
+    gather_rows<C, false>(acc, sr, rw, lane);       // scatter_sum(msg_right, left)[right]
+    gather_rows<C, false>(acc, tb.fl, lw, lane);    // node_ffn_left(h_node[left])
+    gather_rows<C, false>(acc, tb.fr, rw, lane);    // node_ffn_right(h_node[right])
+    layernorm_rows<C, true>(acc, W_(EB_LN_G), W_(EB_LN_BE), lane);
+    store_smem<C>(acc, A, C, warp, lane);
+    tile_gemm<C, C>(acc, A, C, W_(EB_OUT_W), Ws);
+    add_rowvec<C>(acc, W_(EB_OUT_B), lane);
+    combine_smem<C, false>(acc, Es, C, warp, lane);  // h_edge = h_edge + EdgeBlock(.)  graph.py:362
+    store_smem<C>(acc, E2, C, warp, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + warp * 8 + i;
+      if (q < a.n_edges) store_cols<C>(acc[i], tb.hedge + (size_t)q * C, lane);
+    }
+  }
+  if (!a.update_pos) return;
+  // ---- PosUpdate                                                                 graph.py:384-396
+  {
+    float p[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { p[i][0] = 1.f; p[i][1] = 1.f; }
+    gather_rows<C, true>(p, tb.lf, lw, lane);
+    gather_rows<C, true>(p, tb.rf, rw, lane);
+    store_smem<C>(p, P, C, warp, lane);
+  }
+  float w_inter[8], w_gate[8];
+  {
+    float acc[8][8];
+    tile_gemm<C, D>(acc, E2, C, W_(PU_PB_W), Ws);            // edge_lin.bond_linear(h_edge)
+    store_smem<D>(acc, A, D, warp, lane);
+    tile_gemm<C, D>(acc, P, C, W_(PU_PN_W), Ws);             // edge_lin.node_linear(lf * rf)
+    combine_smem<D, true>(acc, A, D, warp, lane);
+    store_smem<D>(acc, A, D, warp, lane);
+    tile_gemm<D, D>(acc, A, D, W_(PU_I1_W), Ws);             // inter_module
+    add_rowvec<D>(acc, W_(PU_I1_B), lane);
+    layernorm_rows<D, true>(acc, W_(PU_I1_G), W_(PU_I1_BE), lane);
+    dot_rows<D>(w_inter, acc, W_(PU_I2_W), lane);
+  }
+  {
+    float g1[8][1];
+    tile_gemm<C, 32>(g1, E2, C, W_(PU_GB_W), Ws);            // gate.net.0: bond | node | time columns
+    tile_gemm<C, 32, true>(g1, P, C, W_(PU_GN_W), Ws);
+    add_rowvec<32>(g1, W_(PU_G1_B), lane);
+    add_scaled_rowvec<32>(g1, W_(PU_GT_W), tes + warp * 8, lane);
+    layernorm_rows<32, true>(g1, W_(PU_G1_G), W_(PU_G1_BE), lane);
+    dot_rows<32>(w_gate, g1, W_(PU_G2_W), lane);
+  }
+  const float b_i2 = W_(PU_I2_B)[0], b_g2 = W_(PU_G2_B)[0];
+  // force = w * rel / d / (d + 1); delta_pos = scatter_sum(force, left)            graph.py:393-394
+  if (lane < 3) {
+    int cur = lw[0];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = warp * 8 + i;
+      const int n = lw[i];
+      const float w = (w_inter[i] + b_i2) * (1.f / (1.f + expf(-(w_gate[i] + b_g2))));
+      const float d = rel[3 * TM + r];
+      const float f = w * rel[lane * TM + r] / d / (d + 1.f);
+      if (n != cur) {
+        if (cur >= 0) atomicAdd(a.pos_nxt + (size_t)cur * 3 + lane, s);
+        cur = n; s = 0.f;
+      }
+      s += f;
+    }
+    if (cur >= 0) atomicAdd(a.pos_nxt + (size_t)cur * 3 + lane, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge decode: half-edge p in caller order -> h_edge[inv[p]] + h_edge[inv[p + Eh]]
+// ------------------------------------------------------------------------------------------------
+struct DecArgs {
+  const float* blob;
+  HeadOff head;
+  Tables tb;
+  const int *left, *right, *inv;
+  int n_half, kind, ke;
+  float* out;   // [Eh][ke]
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1) edge_decode_kernel(const DecArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* Es = smem;               // [64][64]
+  float* A = Es + TM * C;         // [64][64]
+  float* Ws = A + TM * C;
+  int* ls = reinterpret_cast<int*>(Ws + 2 * WCHUNK);
+  int* rs = ls + TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = blockIdx.x * TM;
+  const float* blob = a.blob;
+  const HeadOff& hoff = a.head;
+  const Tables& tb = a.tb;
+  if (tid < TM) {
+    const int p = p0 + tid;
+    int l = -1, r = -1;
+    if (p < a.n_half) { const int q = a.inv[p]; l = a.left[q]; r = a.right[q]; }
+    ls[tid] = l; rs[tid] = r;
+  }
+  for (int i = tid; i < TM * C / 4; i += NTHREADS) {
+    const int r = i / (C / 4), c4 = i % (C / 4);
+    const int p = p0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < a.n_half) {
+      const float4 u = reinterpret_cast<const float4*>(tb.hedge + (size_t)a.inv[p] * C)[c4];
+      const float4 w = reinterpret_cast<const float4*>(tb.hedge + (size_t)a.inv[p + a.n_half] * C)[c4];
+      v = make_float4(u.x + w.x, u.y + w.y, u.z + w.z, u.w + w.w);
+    }
+    reinterpret_cast<float4*>(Es + r * C)[c4] = v;
+  }
+  __syncthreads();
+  float acc[8][2];
+  tile_gemm<C, C>(acc, Es, C, H_(EDEC1_W), Ws);
+  add_rowvec<C>(acc, H_(EDEC1_B), lane);
+  if (a.kind == 2) {   // + W_node (h_node[l] + h_node[r])                           bond_predictor.py:155-160
+    gather_rows<C, false>(acc, tb.dect, ls + warp * 8, lane);
+    gather_rows<C, false>(acc, tb.dect, rs + warp * 8, lane);
+  }
+  layernorm_rows<C, true>(acc, H_(EDEC1_G), H_(EDEC1_BE), lane);
+  store_smem<C>(acc, A, C, warp, lane);
+  float o[8][1];
+  if (a.kind == 2) {
+    tile_gemm<C, C>(acc, A, C, H_(EDEC2_W), Ws);
+    add_rowvec<C>(acc, H_(EDEC2_B), lane);
+    layernorm_rows<C, true>(acc, H_(EDEC3_G), H_(EDEC3_BE), lane);
+    store_smem<C>(acc, A, C, warp, lane);
+    tile_gemm<C, 32>(o, A, C, H_(EDEC3_W), Ws);
+    add_rowvec<32>(o, H_(EDEC3_B), lane);
+  } else {
+    tile_gemm<C, 32>(o, A, C, H_(EDEC2_W), Ws);
+    add_rowvec<32>(o, H_(EDEC2_B), lane);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = p0 + warp * 8 + i;
+    if (p < a.n_half && lane < a.ke) a.out[(size_t)p * a.ke + lane] = o[i][0];
+  }
+}
+
+// kind 0 epilogue: h_edge_out[perm[q]] = hedge[q]
+__global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, const float* __restrict__ hedge,
+                                   float* __restrict__ out) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 6);
+  const int c = threadIdx.x & 63;
+  if (q < n_edges) out[(size_t)perm[q] * C + c] = hedge[(size_t)q * C + c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+
+int fail(int code, const char* fmt, const char* extra = "") {
+  snprintf(g_err, sizeof(g_err), fmt, extra);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                        \
+  do {                                                                        \
+    cudaError_t e_ = (expr);                                                  \
+    if (e_ != cudaSuccess) return fail(MDB_ECUDA, #expr ": %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+inline size_t al(size_t n) { return (n + 31) & ~size_t(31); }
+
+size_t carve(Tables& tb, float* base, int64_t N, int64_t E) {
+  size_t o = 0;
+  auto take = [&](size_t n) { float* p = base ? base + o : nullptr; o += al(n); return p; };
+  tb.x = take(N * D); tb.agg = take(N * D); tb.hn = take(N * D); tb.gx = take(N * D); tb.cen = take(N * D);
+  tb.nll = take(N * 128); tb.nlr = take(N * 128);
+  tb.gnl = take(N * 32); tb.gnr = take(N * 32);
+  tb.fl = take(N * C); tb.fr = take(N * C); tb.lf = take(N * C); tb.rf = take(N * C); tb.dect = take(N * C);
+  tb.slsr = take(4 * N * C);
+  tb.pos0 = take(N * 3); tb.pos1 = take(N * 3);
+  tb.tn = take(N);
+  tb.hedge = take(E * C); tb.ebuf = take(E * C);
+  tb.te = take(E);
+  return o;
+}
+
+constexpr size_t SMEM_NODE = (2 * TM * D + 2 * WCHUNK + TM) * sizeof(float);
+constexpr size_t SMEM_EDGE_B = (TM * C + 2 * TM * D + 2 * WCHUNK + TM + 4 * TM + 2 * TM) * sizeof(float);
+constexpr size_t SMEM_EDGE_D = (3 * TM * C + TM * D + 2 * WCHUNK + TM + 4 * TM + 2 * TM) * sizeof(float);
+constexpr size_t SMEM_DEC = (2 * TM * C + 2 * WCHUNK + 2 * TM) * sizeof(float);
+
+int ensure_attrs() {
+  static bool done = false;
+  if (done) return MDB_OK;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(MDB_EARCH, "moldiff_b200 kernels are built for sm_100a only%s");
+  CUDA_TRY(cudaFuncSetAttribute(node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_NODE));
+  CUDA_TRY(cudaFuncSetAttribute(edge_kernel_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_EDGE_B));
+  CUDA_TRY(cudaFuncSetAttribute(edge_kernel_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_EDGE_D));
+  CUDA_TRY(cudaFuncSetAttribute(edge_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DEC));
+  done = true;
+  return MDB_OK;
+}
+
+void fill_blk(BlkOff& b, const mdb_net_desc* net, int i) {
+  for (int s = 0; s < MDB_NUM_BLOCK_SLOTS; ++s) b.o[s] = (int)net->block_off[i][s];
+}
+
+struct FwdIn {
+  const float *h_node, *pos, *h_edge;          // inputs (meaning depends on kind)
+  const float *node_time, *edge_time;          // kind 0
+  const int64_t *batch_node, *batch_edge, *t;  // kind 1/2
+  float *out_node, *out_pos, *out_edge;        // kind 0: h_node/pos/h_edge; kind 1: preds; kind 2: logits in out_edge
+  int save;                                    // keep per-block inputs for the backward pass
+};
+
+int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, float* workspace,
+                size_t workspace_bytes, cudaStream_t st) {
+  if (!net || !plan || !workspace) return fail(MDB_EINVAL, "null argument%s");
+  const int N = plan->n_nodes, E = plan->n_edges, L = net->num_blocks;
+  if (N <= 0 || E < 0) return fail(MDB_EINVAL, "empty graph%s");
+  if (L < 1 || L > MDB_MAX_BLOCKS) return fail(MDB_EINVAL, "num_blocks out of range%s");
+  if (net->kind != 0 && (plan->n_half * 2 != E)) return fail(MDB_EINVAL, "edges must be (half, flipped half)%s");
+  if (net->num_node_types > 32 || net->num_edge_types > 32) return fail(MDB_EINVAL, "too many types%s");
+  if (net->time_dim < 0 || net->time_dim >= C) return fail(MDB_EINVAL, "time_dim out of range%s");
+  if (mdb_workspace_bytes(N, E, 0, L) > workspace_bytes) return fail(MDB_EINVAL, "workspace too small%s");
+  int rc = ensure_attrs();
+  if (rc) return rc;
+
+  Tables tb;
+  carve(tb, workspace, N, E);
+  HeadOff head;
+  for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
+  const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
+
+  node_init_kernel<<<N, D, 0, st>>>(net->kind, N, net->num_node_types, net->time_dim, net->num_timesteps,
+                                    net->blob, head, in.h_node, in.batch_node, in.t, in.node_time, tb.x, tb.tn);
+  ++g_launches;
+  if (E > 0) {
+    edge_init_kernel<<<(E + 3) / 4, 256, 0, st>>>(net->kind, E, net->num_node_types, net->num_edge_types,
+                                                  net->time_dim, net->num_timesteps, net->blob, head,
+                                                  in.h_edge, in.h_node, in.batch_edge, in.t, in.edge_time,
+                                                  plan->left, plan->right, plan->perm, tb.hedge, tb.te);
+    ++g_launches;
+  }
+  CUDA_TRY(cudaMemsetAsync(tb.agg, 0, (size_t)N * D * sizeof(float), st));
+  CUDA_TRY(cudaMemcpyAsync(tb.pos0, in.pos, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+  const float* pos_cur = tb.pos0;
+  float* pos_nxt = tb.pos1;
+  NodeArgs na;
+  memset(&na, 0, sizeof(na));
+  na.blob = net->blob; na.head = head; na.tb = tb; na.n_nodes = N; na.update_pos = net->update_pos;
+  na.kind = net->kind; na.kn = net->num_node_types; na.pred_node = in.out_node;
+  // pre(0)
+  fill_blk(na.pre, net, 0);
+  na.do_mid = 0; na.do_pre = 1; na.do_dec = 0; na.par_next = 0; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
+  node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na);
+  ++g_launches;
+
+  EdgeArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.blob = net->blob; ea.head = head; ea.tb = tb; ea.left = plan->left; ea.right = plan->right;
+  ea.n_nodes = N; ea.n_edges = E; ea.update_pos = net->update_pos;
+  ea.rbf_lo = net->rbf_start; ea.rbf_hi = net->rbf_stop;
+
+  for (int i = 0; i < L; ++i) {
+    fill_blk(ea.off, net, i);
+    ea.par = i & 1; ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
+    if (E > 0) { edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea); ++g_launches; }
+    fill_blk(na.mid, net, i);
+    na.do_mid = 1; na.do_pre = (i + 1 < L); na.do_dec = (i + 1 == L) && net->kind != 0;
+    if (na.do_pre) fill_blk(na.pre, net, i + 1);
+    na.par_next = (i + 1) & 1; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
+    node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na);
+    ++g_launches;
+    if (E > 0) { edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea); ++g_launches; }
+    if (net->update_pos) { const float* t_ = pos_cur; pos_cur = pos_nxt; pos_nxt = const_cast<float*>(t_); }
+  }
+
+  if (net->kind == 0) {
+    CUDA_TRY(cudaMemcpyAsync(in.out_node, tb.x, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (E > 0) { edge_unsort_kernel<<<(E + 3) / 4, 256, 0, st>>>(E, plan->perm, tb.hedge, in.out_edge); ++g_launches; }
+  } else if (plan->n_half > 0) {
+    DecArgs da;
+    memset(&da, 0, sizeof(da));
+    da.blob = net->blob; da.head = head; da.tb = tb; da.left = plan->left; da.right = plan->right;
+    da.inv = plan->inv; da.n_half = plan->n_half; da.kind = net->kind; da.ke = net->num_edge_types;
+    da.out = in.out_edge;
+    edge_decode_kernel<<<(plan->n_half + TM - 1) / TM, NTHREADS, SMEM_DEC, st>>>(da);
+    ++g_launches;
+  }
+  if (in.out_pos)
+    CUDA_TRY(cudaMemcpyAsync(in.out_pos, pos_cur, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaGetLastError());
+  return MDB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mdb_workspace_bytes(int64_t n_nodes, int64_t n_edges, int32_t with_backward, int32_t num_blocks) {
+  (void)with_backward; (void)num_blocks;
+  Tables tb;
+  return carve(tb, nullptr, n_nodes, n_edges) * sizeof(float);
+}
+
+int mdb_net_forward(const mdb_net_desc* net, const mdb_plan* plan, const float* h_node_in, const float* pos_in,
+                    const float* h_edge_in, const float* node_time, const float* edge_time, float* h_node_out,
+                    float* pos_out, float* h_edge_out, float* workspace, size_t workspace_bytes, void* stream) {
+  if (!net || net->kind != 0) return fail(MDB_EINVAL, "mdb_net_forward needs a kind-0 descriptor%s");
+  FwdIn in;
+  memset(&in, 0, sizeof(in));
+  in.h_node = h_node_in; in.pos = pos_in; in.h_edge = h_edge_in; in.node_time = node_time; in.edge_time = edge_time;
+  in.out_node = h_node_out; in.out_pos = pos_out; in.out_edge = h_edge_out;
+  return run_forward(net, plan, in, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mdb_moldiff_forward(const mdb_net_desc* net, const mdb_plan* plan, const float* h_node_pert,
+                        const float* pos_pert, const float* h_edge_pert, const int64_t* batch_node,
+                        const int64_t* batch_edge, const int64_t* t, float* pred_node, float* pred_pos,
+                        float* pred_halfedge, float* workspace, size_t workspace_bytes, void* stream) {
+  if (!net || net->kind != 1) return fail(MDB_EINVAL, "mdb_moldiff_forward needs a kind-1 descriptor%s");
+  FwdIn in;
+  memset(&in, 0, sizeof(in));
+  in.h_node = h_node_pert; in.pos = pos_pert; in.h_edge = h_edge_pert;
+  in.batch_node = batch_node; in.batch_edge = batch_edge; in.t = t;
+  in.out_node = pred_node; in.out_pos = pred_pos; in.out_edge = pred_halfedge;
+  return run_forward(net, plan, in, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mdb_bondpred_forward(const mdb_net_desc* net, const mdb_plan* plan, const float* h_node, const float* pos,
+                         const int64_t* batch_node, const int64_t* batch_edge, const int64_t* t, float* logits,
+                         int32_t save_for_backward, float* workspace, size_t workspace_bytes, void* stream) {
+  if (!net || net->kind != 2) return fail(MDB_EINVAL, "mdb_bondpred_forward needs a kind-2 descriptor%s");
+  FwdIn in;
+  memset(&in, 0, sizeof(in));
+  in.h_node = h_node; in.pos = pos; in.h_edge = nullptr;
+  in.batch_node = batch_node; in.batch_edge = batch_edge; in.t = t;
+  in.out_edge = logits;
+  in.save = save_for_backward;
+  return run_forward(net, plan, in, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mdb_bondpred_backward(const mdb_net_desc*, const mdb_plan*, const float*, const float*, const int64_t*,
+                          const int64_t*, const int64_t*, const float*, float*, float*, size_t, void*) {
+  return fail(MDB_EINVAL, "mdb_bondpred_backward: backward kernels not built yet%s");
+}
+
+const char* mdb_last_error(void) { return g_err; }
+int mdb_version(void) { return 1; }
+int64_t mdb_launch_count(void) { return g_launches; }
+
+}  // extern "C"

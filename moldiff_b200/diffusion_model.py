@@ -1,0 +1,267 @@
+"""``MolDiff`` -- the joint (atom type, position, bond type) diffusion model, B200-native.
+
+Drop-in for ``models.model.MolDiff`` (reference ``models/model.py:12-378``): same constructor
+``MolDiff(config, num_node_types, num_edge_types)``, same ``forward`` / ``sample`` / ``get_loss`` /
+``add_noise`` signatures and return structures, same ``state_dict`` schema (581 keys).  What differs is
+where the arithmetic runs: ``forward`` is ONE C-ABI call (``mdb_moldiff_forward``: embedders + 6
+NodeEdgeNet blocks + decoders as hand-written sm_100a kernels); the guidance term of ``sample`` is the
+bond predictor's CUDA forward + hand-written input-gradient backward.  The noise schedule / posterior
+sampling around it stays host-side PyTorch (north_star), operating on device tensors.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import engine
+from .nets import MLP, GaussianSmearing, NodeEdgeNet
+from .schedules import get_beta_schedule
+from .transitions import CategoricalTransition, GaussianTransition, gumbel_argmax
+
+
+def _cfg_get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def build_transitions(owner, diff_cfg, num_node_types, num_edge_types, with_edges=True):
+    """Shared by MolDiff and BondPredictor (model.py:49-95, bond_predictor.py:40-73)."""
+    owner.num_timesteps = diff_cfg["num_timesteps"]
+    owner.categorical_space = _cfg_get(diff_cfg, "categorical_space", "discrete")
+    if owner.categorical_space == "continuous":
+        owner.scaling = _cfg_get(diff_cfg, "scaling", [1.0, 1.0, 1.0])
+    else:
+        owner.scaling = [1.0, 1.0, 1.0]
+    if owner.scaling[0] != 1:
+        raise AssertionError("scaling for pos should be 1")
+    T = owner.num_timesteps
+    owner.pos_transition = GaussianTransition(get_beta_schedule(num_timesteps=T, **diff_cfg["diff_pos"]))
+    specs = [("node_transition", "diff_atom", num_node_types, 1)]
+    if with_edges:
+        specs.append(("edge_transition", "diff_bond", num_edge_types, 2))
+    for attr, key, k, si in specs:
+        betas = get_beta_schedule(num_timesteps=T, **diff_cfg[key])
+        if owner.categorical_space == "discrete":
+            tr = CategoricalTransition(betas, k, init_prob=diff_cfg[key]["init_prob"])
+        elif owner.categorical_space == "continuous":
+            tr = GaussianTransition(betas, k, owner.scaling[si])
+        else:
+            raise ValueError(owner.categorical_space)
+        setattr(owner, attr, tr)
+
+
+class _PackedMixin:
+    """Lazily packs the module's weights into the kernel layout; re-packs when any parameter was
+    modified in place (optimizer step, load_state_dict) or moved (.to())."""
+
+    def _packed_net(self, device):
+        params = list(self.parameters()) + list(self.buffers())
+        key = (str(device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        if getattr(self, "_packed", None) is None or self._packed_key != key:
+            self._packed = self._pack(device)
+            self._packed_key = key
+        return self._packed
+
+
+class MolDiff(nn.Module, _PackedMixin):
+    def __init__(self, config, num_node_types, num_edge_types, **kwargs):
+        super().__init__()
+        self.config = config
+        self.num_node_types = num_node_types
+        self.num_edge_types = num_edge_types
+        self.bond_len_loss = _cfg_get(config, "bond_len_loss", False)
+        build_transitions(self, config["diff"], num_node_types, num_edge_types)
+
+        node_dim, edge_dim = config["node_dim"], config["edge_dim"]
+        time_dim = config["diff"]["time_dim"]
+        self.node_embedder = nn.Linear(num_node_types, node_dim - time_dim, bias=False)
+        self.edge_embedder = nn.Linear(num_edge_types, edge_dim - time_dim, bias=False)
+        self.time_emb = nn.Sequential(GaussianSmearing(stop=self.num_timesteps, num_gaussians=time_dim, type_="linear"))
+        den = dict(config["denoiser"])
+        if den.get("backbone") != "NodeEdgeNet":
+            raise NotImplementedError(den.get("backbone"))
+        self.denoiser = NodeEdgeNet(node_dim, edge_dim, **den)
+        self.node_decoder = MLP(node_dim, num_node_types, node_dim)
+        self.edge_decoder = MLP(edge_dim, num_edge_types, edge_dim)
+        self.time_dim = time_dim
+        self._packed = None
+        self._packed_key = None
+
+    # ---- weights ----
+    def _pack(self, device):
+        return engine.PackedNet(self.state_dict(), kind=1, net_prefix="denoiser", num_blocks=self.denoiser.num_blocks,
+                                update_pos=self.denoiser.update_pos, cutoff=self.denoiser.cutoff,
+                                start=self.denoiser.start, time_dim=self.time_dim,
+                                num_node_types=self.num_node_types, num_edge_types=self.num_edge_types,
+                                num_timesteps=self.num_timesteps, device=device)
+
+    # ---- reference API ----
+    def sample_time(self, num_graphs, device, **kwargs):
+        """Antithetic timestep pairs (model.py:97-104)."""
+        half = torch.randint(0, self.num_timesteps, size=(num_graphs // 2 + 1,), device=device)
+        time_step = torch.cat([half, self.num_timesteps - half - 1], dim=0)[:num_graphs]
+        return time_step, torch.ones_like(time_step).float() / self.num_timesteps
+
+    def _perturb(self, node_type, node_pos, batch_node, halfedge_type, batch_halfedge, time_step):
+        pos_pert = self.pos_transition.add_noise(node_pos, time_step, batch_node)
+        node_pert = self.node_transition.add_noise(node_type, time_step, batch_node)
+        half_pert = self.edge_transition.add_noise(halfedge_type, time_step, batch_halfedge)
+        return pos_pert, node_pert, half_pert
+
+    def add_noise(self, node_type, node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge,
+                  num_mol, t, bond_predictor=None, **kwargs):
+        time_step = t * torch.ones(num_mol, device=node_pos.device).long()
+        pos_pert, node_pert, half_pert = self._perturb(node_type, node_pos, batch_node, halfedge_type,
+                                                       batch_halfedge, time_step)
+        return [node_pert[0], pos_pert, half_pert[0]]
+
+    def forward(self, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t):
+        """Predict the clean molecule from its perturbed version at step t (model.py:204-234)."""
+        plan = engine.plan_for(edge_index, h_node_pert.shape[0])
+        net = self._packed_net(pos_pert.device)
+        pred_node, pred_pos, pred_half = engine.moldiff_forward(
+            net, plan, h_node_pert, pos_pert, h_edge_pert, batch_node, batch_edge, t)
+        return {"pred_node": pred_node, "pred_pos": pred_pos, "pred_halfedge": pred_half}
+
+    def get_loss(self, node_type, node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge, num_mol):
+        """Forward + diffusion losses (model.py:128-201).  The fused forward does not record an autograd
+        graph: the returned losses are values (training backward is a later-round row)."""
+        device = node_pos.device
+        time_step, _ = self.sample_time(num_mol, device)
+        pos_pert, node_pert, half_pert = self._perturb(node_type, node_pos, batch_node, halfedge_type,
+                                                       batch_halfedge, time_step)
+        edge_index = torch.cat([halfedge_index, halfedge_index.flip(0)], dim=1)
+        batch_edge = torch.cat([batch_halfedge, batch_halfedge], dim=0)
+        discrete = self.categorical_space == "discrete"
+        if discrete:
+            h_node_pert, log_node_t, log_node_0 = node_pert
+            h_half_pert, log_half_t, log_half_0 = half_pert
+        else:
+            h_node_pert, h_node_0 = node_pert
+            h_half_pert, h_half_0 = half_pert
+        preds = self(h_node_pert, pos_pert, batch_node, torch.cat([h_half_pert, h_half_pert], dim=0),
+                     edge_index, batch_edge, time_step)
+        pred_node, pred_pos, pred_half = preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]
+
+        out = {}
+        loss_pos = F.mse_loss(pred_pos, node_pos)
+        if self.bond_len_loss == True:  # noqa: E712  (config value, as in the reference)
+            bond = halfedge_index[:, halfedge_type > 0]
+            true_len = torch.norm(node_pos[bond[0]] - node_pos[bond[1]], dim=-1)
+            pred_len = torch.norm(pred_pos[bond[0]] - pred_pos[bond[1]], dim=-1)
+            out["loss_len"] = F.mse_loss(pred_len, true_len)
+        if discrete:
+            def vb_term(tr, logits, log_t, log_0, batch):
+                log_recon = F.log_softmax(logits, dim=-1)
+                post_true = tr.q_v_posterior(log_0, log_t, time_step, batch, v0_prob=True)
+                post_pred = tr.q_v_posterior(log_recon, log_t, time_step, batch, v0_prob=True)
+                return torch.mean(tr.compute_v_Lt(post_true, post_pred, log_0, t=time_step, batch=batch)) * 100
+            loss_node = vb_term(self.node_transition, pred_node, log_node_t, log_node_0, batch_node)
+            loss_edge = vb_term(self.edge_transition, pred_half, log_half_t, log_half_0, batch_halfedge)
+        else:
+            loss_node = F.mse_loss(pred_node, h_node_0) * 30
+            loss_edge = F.mse_loss(pred_half, h_half_0) * 30
+        total = loss_pos + loss_node + loss_edge + (out["loss_len"] if "loss_len" in out else 0)
+        return {"loss": total, "loss_pos": loss_pos, "loss_node": loss_node, "loss_edge": loss_edge, **out}
+
+    # ---- sampling ----
+    def _guidance_delta(self, bond_predictor, gui_type, gui_scale, h_node_pert, pos_pert, batch_node,
+                        edge_index, batch_edge, time_step, halfedge_type_prev, log_halfedge_type):
+        """-d objective / d pos * scale (model.py:309-361).  The bond predictor's forward AND its backward
+        with respect to the positions are CUDA kernels; autograd only differentiates the scalar objective
+        with respect to the [Eh, K] logits."""
+        with torch.enable_grad():
+            pos_in = pos_pert.detach().requires_grad_(True)
+            logits = bond_predictor(h_node_pert.detach(), pos_in, batch_node, edge_index, batch_edge, time_step)
+            sign = -1.0
+            if gui_type in ("entropy", "entropy_bond"):
+                prob = torch.softmax(logits, dim=-1)
+                ent = (-torch.sum(prob * torch.log(prob + 1e-12), dim=-1)).log()
+                obj = ent.sum() if gui_type == "entropy" else (ent * prob[:, 1:].detach().sum(dim=-1)).sum()
+            elif gui_type in ("uncertainty", "uncertainty_bond"):
+                unc = torch.sigmoid(-torch.logsumexp(logits, dim=-1)).log()
+                if gui_type == "uncertainty":
+                    obj = unc.sum()
+                else:
+                    obj = (unc * torch.softmax(logits, dim=-1)[:, 1:].detach().sum(dim=-1)).sum()
+            elif gui_type in ("logit_bond", "logit"):
+                keep = ((halfedge_type_prev >= 1) & (halfedge_type_prev <= 4)) if gui_type == "logit_bond" \
+                    else (halfedge_type_prev <= 4)
+                idx = keep.nonzero().squeeze(-1)
+                obj = logits[idx, halfedge_type_prev[idx]].sum()
+                sign = 1.0
+            elif gui_type in ("crossent", "crossent_bond"):
+                if gui_type == "crossent":
+                    ce = F.cross_entropy(logits, log_halfedge_type.exp()[:, :-1], reduction="none")
+                else:
+                    ce = F.cross_entropy(logits[:, 1:], log_halfedge_type.exp()[:, 1:-1], reduction="none")
+                obj = ce.log().sum()
+            else:
+                raise NotImplementedError(f"Guidance type {gui_type} is not implemented")
+            grad = torch.autograd.grad(obj, pos_in)[0]
+        return sign * grad * gui_scale
+
+    @torch.no_grad()
+    def sample(self, n_graphs, batch_node, halfedge_index, batch_halfedge, bond_predictor=None, guidance=None,
+               progress=False):
+        """T-step ancestral sampling (model.py:236-378).  Returns {'pred': [node, pos, halfedge] of the
+        last step, 'traj': [node_traj, pos_traj, halfedge_traj]} exactly like the reference."""
+        device = batch_node.device
+        n_nodes, n_half = len(batch_node), len(batch_halfedge)
+        T = self.num_timesteps
+        discrete = self.categorical_space == "discrete"
+
+        node_init = self.node_transition.sample_init(n_nodes)
+        pos = self.pos_transition.sample_init([n_nodes, 3])
+        half_init = self.edge_transition.sample_init(n_half)
+        if discrete:
+            _, h_node, log_node = node_init
+            _, h_half, log_half = half_init
+        else:
+            h_node, h_half = node_init, half_init
+
+        node_traj = torch.zeros([T + 1, n_nodes, h_node.shape[-1]], dtype=h_node.dtype, device=device)
+        pos_traj = torch.zeros([T + 1, n_nodes, 3], dtype=pos.dtype, device=device)
+        half_traj = torch.zeros([T + 1, n_half, h_half.shape[-1]], dtype=h_half.dtype, device=device)
+        node_traj[0], pos_traj[0], half_traj[0] = h_node, pos, h_half
+
+        edge_index = torch.cat([halfedge_index, halfedge_index.flip(0)], dim=1)
+        batch_edge = torch.cat([batch_halfedge, batch_halfedge], dim=0)
+        steps = range(T - 1, -1, -1)
+        if progress:
+            from tqdm import tqdm
+            steps = tqdm(steps, total=T)
+        pred_node = pred_pos = pred_half = None
+        for i, step in enumerate(steps):
+            time_step = torch.full((n_graphs,), step, dtype=torch.long, device=device)
+            preds = self(h_node, pos, batch_node, torch.cat([h_half, h_half], dim=0), edge_index, batch_edge, time_step)
+            pred_node, pred_pos, pred_half = preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]
+
+            pos_prev = self.pos_transition.get_prev_from_recon(x_t=pos, x_recon=pred_pos, t=time_step, batch=batch_node)
+            half_type_prev = None
+            if discrete:
+                log_node = self.node_transition.q_v_posterior(F.log_softmax(pred_node, dim=-1), log_node,
+                                                              time_step, batch_node, v0_prob=True)
+                h_node_prev = self.node_transition.onehot_encode(gumbel_argmax(log_node))
+                log_half = self.edge_transition.q_v_posterior(F.log_softmax(pred_half, dim=-1), log_half,
+                                                              time_step, batch_halfedge, v0_prob=True)
+                half_type_prev = gumbel_argmax(log_half)
+                h_half_prev = self.edge_transition.onehot_encode(half_type_prev)
+            else:
+                h_node_prev = self.node_transition.get_prev_from_recon(x_t=h_node, x_recon=pred_node, t=time_step,
+                                                                       batch=batch_node)
+                h_half_prev = self.edge_transition.get_prev_from_recon(x_t=h_half, x_recon=pred_half, t=time_step,
+                                                                       batch=batch_halfedge)
+            if guidance is not None:
+                gui_type, gui_scale = guidance
+                if gui_scale > 0:
+                    pos_prev = pos_prev + self._guidance_delta(
+                        bond_predictor, gui_type, gui_scale, h_node, pos, batch_node, edge_index, batch_edge,
+                        time_step, half_type_prev, log_half if discrete else None)
+
+            node_traj[i + 1], pos_traj[i + 1], half_traj[i + 1] = h_node_prev, pos_prev, h_half_prev
+            h_node, pos, h_half = h_node_prev, pos_prev, h_half_prev
+
+        return {"pred": [pred_node, pred_pos, pred_half], "traj": [node_traj, pos_traj, half_traj]}

@@ -1,0 +1,279 @@
+"""Host binding of the C-ABI (include/moldiff_b200.h) -- ctypes, raw device pointers, no torch types
+across the boundary.  PyTorch is used here only for device memory, streams and the once-per-batch sort.
+
+There is deliberately NO fallback: if ``libmoldiff_b200.so`` is missing or the tensors are not on a
+CUDA device, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from . import packing
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmoldiff_b200.so")
+_lib = None
+_lib_lock = threading.Lock()
+
+NUM_HEAD = len(packing.HEAD_SLOTS)
+NUM_BLOCK = len(packing.BLOCK_SLOTS)
+MAX_BLOCKS = packing.MAX_BLOCKS
+
+
+class NetDesc(C.Structure):
+    _fields_ = [
+        ("blob", C.c_void_p),
+        ("num_blocks", C.c_int32),
+        ("update_pos", C.c_int32),
+        ("rbf_start", C.c_float),
+        ("rbf_stop", C.c_float),
+        ("time_dim", C.c_int32),
+        ("num_node_types", C.c_int32),
+        ("num_edge_types", C.c_int32),
+        ("num_timesteps", C.c_float),
+        ("kind", C.c_int32),
+        ("head_off", C.c_int64 * NUM_HEAD),
+        ("block_off", (C.c_int64 * NUM_BLOCK) * MAX_BLOCKS),
+    ]
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32),
+        ("n_edges", C.c_int32),
+        ("n_half", C.c_int32),
+        ("left", C.c_void_p),
+        ("right", C.c_void_p),
+        ("perm", C.c_void_p),
+        ("inv", C.c_void_p),
+    ]
+
+
+class MoldiffB200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen the in-tree shared library and declare its prototypes.  Raises if it is not built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise MoldiffB200Error(
+                f"{_LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "moldiff_b200 has no CPU / eager fallback")
+        lib = C.CDLL(_LIB_PATH)
+        vp, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+        lib.mdb_workspace_bytes.restype = sz
+        lib.mdb_workspace_bytes.argtypes = [i64, i64, i32, i32]
+        lib.mdb_net_forward.restype = C.c_int
+        lib.mdb_net_forward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 9 + [sz, vp]
+        lib.mdb_moldiff_forward.restype = C.c_int
+        lib.mdb_moldiff_forward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 10 + [sz, vp]
+        lib.mdb_bondpred_forward.restype = C.c_int
+        lib.mdb_bondpred_forward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 6 + [i32, vp, sz, vp]
+        lib.mdb_bondpred_backward.restype = C.c_int
+        lib.mdb_bondpred_backward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 8 + [sz, vp]
+        lib.mdb_last_error.restype = C.c_char_p
+        lib.mdb_version.restype = C.c_int
+        lib.mdb_launch_count.restype = i64
+        _lib = lib
+        return lib
+
+
+def launch_count():
+    return int(load_library().mdb_launch_count())
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load_library().mdb_last_error().decode()
+        raise MoldiffB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def _dev_f32(t, name):
+    if not t.is_cuda:
+        raise MoldiffB200Error(f"{name} must be a CUDA tensor: moldiff_b200 has no CPU path")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _dev_i64(t, name):
+    if not t.is_cuda:
+        raise MoldiffB200Error(f"{name} must be a CUDA tensor: moldiff_b200 has no CPU path")
+    return t.to(torch.int64).contiguous()
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class PackedNet:
+    """Device-resident packed weights + the mdb_net_desc that describes them."""
+
+    def __init__(self, state_dict, *, kind, net_prefix, num_blocks, update_pos, cutoff, start=0.0,
+                 time_dim=0, num_node_types=0, num_edge_types=0, num_timesteps=1.0, device=None):
+        blob, head_off, block_off = packing.pack_network(
+            state_dict, kind=kind, net_prefix=net_prefix, num_blocks=num_blocks,
+            update_pos=update_pos, time_dim=time_dim)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise MoldiffB200Error("PackedNet needs a CUDA device: moldiff_b200 has no CPU path")
+        self.blob = blob.to(self.device)
+        d = NetDesc()
+        d.blob = self.blob.data_ptr()
+        d.num_blocks = num_blocks
+        d.update_pos = int(bool(update_pos))
+        d.rbf_start = float(start)
+        d.rbf_stop = float(cutoff)
+        d.time_dim = int(time_dim)
+        d.num_node_types = int(num_node_types)
+        d.num_edge_types = int(num_edge_types)
+        d.num_timesteps = float(num_timesteps)
+        d.kind = int(kind)
+        for i, o in enumerate(head_off):
+            d.head_off[i] = o
+        for b in range(MAX_BLOCKS):
+            for s in range(NUM_BLOCK):
+                d.block_off[b][s] = block_off[b][s] if b < num_blocks else -1
+        self.desc = d
+        self.kind = kind
+        self.num_blocks = num_blocks
+
+
+class GraphPlan:
+    """CSR edge order for one batch: edges sorted by (left, right).  Constant over all T steps."""
+
+    def __init__(self, edge_index, n_nodes, paired_halves=True):
+        if not edge_index.is_cuda:
+            raise MoldiffB200Error("edge_index must be a CUDA tensor: moldiff_b200 has no CPU path")
+        ei = edge_index.to(torch.int64)
+        E = int(ei.shape[1])
+        if n_nodes >= 2 ** 31 or E >= 2 ** 31:
+            raise MoldiffB200Error("graph too large for int32 indexing")
+        key = ei[0] * int(n_nodes) + ei[1]
+        perm = torch.argsort(key, stable=True)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(E, device=ei.device)
+        self.left = ei[0][perm].to(torch.int32).contiguous()
+        self.right = ei[1][perm].to(torch.int32).contiguous()
+        self.perm = perm.to(torch.int32).contiguous()
+        self.inv = inv.to(torch.int32).contiguous()
+        self.n_nodes, self.n_edges = int(n_nodes), E
+        self.n_half = E // 2 if (paired_halves and E % 2 == 0) else 0
+        self.device = ei.device
+        p = Plan()
+        p.n_nodes, p.n_edges, p.n_half = self.n_nodes, self.n_edges, self.n_half
+        p.left, p.right = self.left.data_ptr(), self.right.data_ptr()
+        p.perm, p.inv = self.perm.data_ptr(), self.inv.data_ptr()
+        self.c = p
+        self._workspace = {}
+
+    def workspace(self, with_backward, num_blocks):
+        key = (int(with_backward), int(num_blocks))
+        ws = self._workspace.get(key)
+        if ws is None:
+            nbytes = load_library().mdb_workspace_bytes(self.n_nodes, self.n_edges, key[0], key[1])
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            self._workspace[key] = ws
+        return ws
+
+
+_plan_cache = {}
+
+
+def plan_for(edge_index, n_nodes):
+    """Plans are cached on the identity + version of the edge_index tensor: MolDiff.sample reuses one
+    edge_index for all T steps, so the sort runs once per batch."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(n_nodes), str(edge_index.device))
+    hit = _plan_cache.get("k")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    plan = GraphPlan(edge_index, n_nodes)
+    _plan_cache["k"] = (key, plan, edge_index)   # keep edge_index alive so data_ptr cannot be recycled
+    return plan
+
+
+def net_forward(net: PackedNet, plan: GraphPlan, h_node, pos, h_edge, node_time, edge_time):
+    lib = load_library()
+    h_node, pos, h_edge = _dev_f32(h_node, "h_node"), _dev_f32(pos, "pos_node"), _dev_f32(h_edge, "h_edge")
+    node_time = _dev_f32(node_time, "node_time").reshape(-1)
+    edge_time = _dev_f32(edge_time, "edge_time").reshape(-1)
+    N, E = plan.n_nodes, plan.n_edges
+    if h_node.shape != (N, packing.NODE_DIM) or h_edge.shape != (E, packing.EDGE_DIM) or pos.shape != (N, 3):
+        raise MoldiffB200Error(f"shape mismatch: h_node {tuple(h_node.shape)}, h_edge {tuple(h_edge.shape)}, "
+                               f"pos {tuple(pos.shape)} for N={N}, E={E} (kernels are built for 256/64)")
+    out_node, out_pos, out_edge = torch.empty_like(h_node), torch.empty_like(pos), torch.empty_like(h_edge)
+    ws = plan.workspace(0, net.num_blocks)
+    rc = lib.mdb_net_forward(C.byref(net.desc), C.byref(plan.c), h_node.data_ptr(), pos.data_ptr(),
+                             h_edge.data_ptr(), node_time.data_ptr(), edge_time.data_ptr(),
+                             out_node.data_ptr(), out_pos.data_ptr(), out_edge.data_ptr(),
+                             ws.data_ptr(), ws.numel() * 4, _stream_ptr(h_node.device))
+    _check(rc, "mdb_net_forward")
+    return out_node, out_pos, out_edge
+
+
+def moldiff_forward(net: PackedNet, plan: GraphPlan, h_node_pert, pos_pert, h_edge_pert, batch_node, batch_edge, t):
+    lib = load_library()
+    h_node_pert, pos_pert = _dev_f32(h_node_pert, "h_node_pert"), _dev_f32(pos_pert, "pos_pert")
+    h_edge_pert = _dev_f32(h_edge_pert, "h_edge_pert")
+    batch_node, batch_edge, t = _dev_i64(batch_node, "batch_node"), _dev_i64(batch_edge, "batch_edge"), _dev_i64(t, "t")
+    N, E = plan.n_nodes, plan.n_edges
+    kn, ke = net.desc.num_node_types, net.desc.num_edge_types
+    if h_node_pert.shape != (N, kn) or h_edge_pert.shape != (E, ke) or pos_pert.shape != (N, 3):
+        raise MoldiffB200Error("MolDiff.forward: input shapes do not match the graph plan / type counts")
+    dev = pos_pert.device
+    pred_node = torch.empty(N, kn, dtype=torch.float32, device=dev)
+    pred_pos = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    pred_half = torch.empty(E // 2, ke, dtype=torch.float32, device=dev)
+    ws = plan.workspace(0, net.num_blocks)
+    rc = lib.mdb_moldiff_forward(C.byref(net.desc), C.byref(plan.c), h_node_pert.data_ptr(), pos_pert.data_ptr(),
+                                 h_edge_pert.data_ptr(), batch_node.data_ptr(), batch_edge.data_ptr(), t.data_ptr(),
+                                 pred_node.data_ptr(), pred_pos.data_ptr(), pred_half.data_ptr(),
+                                 ws.data_ptr(), ws.numel() * 4, _stream_ptr(dev))
+    _check(rc, "mdb_moldiff_forward")
+    return pred_node, pred_pos, pred_half
+
+
+def bondpred_forward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, batch_edge, t, save=False):
+    lib = load_library()
+    h_node, pos = _dev_f32(h_node, "h_node"), _dev_f32(pos, "pos_node")
+    batch_node, batch_edge, t = _dev_i64(batch_node, "batch_node"), _dev_i64(batch_edge, "batch_edge"), _dev_i64(t, "t")
+    N, E = plan.n_nodes, plan.n_edges
+    if h_node.shape != (N, net.desc.num_node_types) or pos.shape != (N, 3):
+        raise MoldiffB200Error("BondPredictor.forward: input shapes do not match the graph plan / type counts")
+    logits = torch.empty(E // 2, net.desc.num_edge_types, dtype=torch.float32, device=pos.device)
+    ws = plan.workspace(1 if save else 0, net.num_blocks)
+    rc = lib.mdb_bondpred_forward(C.byref(net.desc), C.byref(plan.c), h_node.data_ptr(), pos.data_ptr(),
+                                  batch_node.data_ptr(), batch_edge.data_ptr(), t.data_ptr(), logits.data_ptr(),
+                                  1 if save else 0, ws.data_ptr(), ws.numel() * 4, _stream_ptr(pos.device))
+    _check(rc, "mdb_bondpred_forward")
+    return logits
+
+
+def bondpred_backward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, batch_edge, t, d_logits):
+    """d(sum(logits * d_logits)) / d pos through the bond predictor (hand-written backward kernels).  Must
+    follow bondpred_forward(save=True) with the same inputs (the autograd.Function guarantees it)."""
+    lib = load_library()
+    h_node, pos = _dev_f32(h_node, "h_node"), _dev_f32(pos, "pos_node")
+    d_logits = _dev_f32(d_logits, "d_logits")
+    batch_node, batch_edge, t = _dev_i64(batch_node, "batch_node"), _dev_i64(batch_edge, "batch_edge"), _dev_i64(t, "t")
+    if d_logits.shape != (plan.n_edges // 2, net.desc.num_edge_types):
+        raise MoldiffB200Error("bondpred_backward: d_logits shape mismatch")
+    d_pos = torch.empty(plan.n_nodes, 3, dtype=torch.float32, device=pos.device)
+    ws = plan.workspace(1, net.num_blocks)
+    rc = lib.mdb_bondpred_backward(C.byref(net.desc), C.byref(plan.c), h_node.data_ptr(), pos.data_ptr(),
+                                   batch_node.data_ptr(), batch_edge.data_ptr(), t.data_ptr(),
+                                   d_logits.data_ptr(), d_pos.data_ptr(),
+                                   ws.data_ptr(), ws.numel() * 4, _stream_ptr(pos.device))
+    _check(rc, "mdb_bondpred_backward")
+    return d_pos

@@ -1,0 +1,192 @@
+"""Weight packing: reference-schema ``state_dict`` -> one fp32 blob in the kernel layout.
+
+The slot lists are parsed from ``include/moldiff_b200.h`` (the X-macro lists are the ABI), so the
+Python packer and the CUDA kernels cannot drift apart.  Every matrix is stored ``[K][N]`` row-major
+(= ``Linear.weight.T``); first-layer Linears that act on a concatenation ``[edge ; node ; time]`` are
+split column-wise so the per-node part can be hoisted out of the per-edge work (exact, by linearity
+-- SURVEY.md section 7.1).  State-dict key names cited below are the reference's
+(``models/graph.py:12-27,123-131,252-266,378-382``).
+"""
+from __future__ import annotations
+
+import os
+import re
+
+import torch
+
+_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "moldiff_b200.h")
+NODE_DIM, EDGE_DIM, NUM_RBF, MAX_BLOCKS = 256, 64, 16, 16
+_ALIGN = 32  # floats (128 B): keeps every slot 16-byte aligned for cp.async / float4 loads
+
+
+def _parse_slots(macro):
+    src = open(_HEADER).read()
+    m = re.search(r"#define\s+" + macro + r"\(X\)(.*?)\n\n", src, re.S)
+    if not m:
+        raise RuntimeError(f"{macro} not found in {_HEADER}")
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    return re.findall(r"X\((\w+)\)", body)
+
+
+BLOCK_SLOTS = _parse_slots("MDB_BLOCK_SLOTS")
+HEAD_SLOTS = _parse_slots("MDB_HEAD_SLOTS")
+
+
+def _t(w):
+    """Linear.weight [out][in] -> [in][out] contiguous fp32."""
+    return w.detach().to(torch.float32).t().contiguous()
+
+
+def _pad_cols(m, n):
+    out = torch.zeros(m.shape[0], n, dtype=torch.float32)
+    out[:, : m.shape[1]] = m
+    return out
+
+
+def _pad_vec(v, n):
+    out = torch.zeros(n, dtype=torch.float32)
+    out[: v.shape[0]] = v.detach().float()
+    return out
+
+
+def _mlp2(sd, p, tag, out):
+    """MLP(in -> hidden -> out): net.0 Linear, net.1 LayerNorm, net.3 Linear (common.py:184-198)."""
+    out[f"{tag}1_W"] = _t(sd[f"{p}.net.0.weight"])
+    out[f"{tag}1_B"] = sd[f"{p}.net.0.bias"]
+    out[f"{tag}1_G"] = sd[f"{p}.net.1.weight"]
+    out[f"{tag}1_BE"] = sd[f"{p}.net.1.bias"]
+    out[f"{tag}2_W"] = _t(sd[f"{p}.net.3.weight"])
+    out[f"{tag}2_B"] = sd[f"{p}.net.3.bias"]
+
+
+def _bond_ffn(sd, p, tag, out, bond_dim, node_dim):
+    """BondFFN (graph.py:123-131); gate.net.0 acts on cat[bond(bond_dim) ; node(node_dim) ; time(1)]."""
+    out[f"{tag}_BL_W" if tag != "PU" else "PU_PB_W"] = _t(sd[f"{p}.bond_linear.weight"])
+    out[f"{tag}_NL_W" if tag != "PU" else "PU_PN_W"] = _t(sd[f"{p}.node_linear.weight"])
+    out[f"{tag}_I1_W"] = _t(sd[f"{p}.inter_module.net.0.weight"])
+    out[f"{tag}_I1_B"] = sd[f"{p}.inter_module.net.0.bias"]
+    out[f"{tag}_I1_G"] = sd[f"{p}.inter_module.net.1.weight"]
+    out[f"{tag}_I1_BE"] = sd[f"{p}.inter_module.net.1.bias"]
+    out[f"{tag}_I2_W"] = _t(sd[f"{p}.inter_module.net.3.weight"])
+    out[f"{tag}_I2_B"] = sd[f"{p}.inter_module.net.3.bias"]
+    g0 = sd[f"{p}.gate.net.0.weight"]  # [32][bond_dim + node_dim + 1]
+    out[f"{tag}_GB_W"] = _t(g0[:, :bond_dim])
+    out[f"{tag}_GN_W"] = _t(g0[:, bond_dim:bond_dim + node_dim])
+    out[f"{tag}_GT_W"] = g0[:, bond_dim + node_dim]
+    out[f"{tag}_G1_B"] = sd[f"{p}.gate.net.0.bias"]
+    out[f"{tag}_G1_G"] = sd[f"{p}.gate.net.1.weight"]
+    out[f"{tag}_G1_BE"] = sd[f"{p}.gate.net.1.bias"]
+    out[f"{tag}_G2_W"] = _t(sd[f"{p}.gate.net.3.weight"])
+    out[f"{tag}_G2_B"] = sd[f"{p}.gate.net.3.bias"]
+
+
+def block_tensors(sd, net_prefix, i, update_pos):
+    """All slot tensors of block i, keyed by slot name."""
+    o = {}
+    o["EE_W"] = _t(sd[f"{net_prefix}.edge_embs.{i}.weight"])        # [80][64]
+    o["EE_B"] = sd[f"{net_prefix}.edge_embs.{i}.bias"]
+    nb = f"{net_prefix}.node_blocks_with_edge.{i}"
+    _mlp2(sd, nb + ".node_net", "NB_NN", o)
+    _mlp2(sd, nb + ".edge_net", "NB_EN", o)
+    o["NB_MSG_W"] = _t(sd[nb + ".msg_net.weight"])
+    o["NB_MSG_B"] = sd[nb + ".msg_net.bias"]
+    g0 = sd[nb + ".gate.net.0.weight"]                              # [256][64 + 256 + 1]   graph.py:22,46
+    o["NB_GE_W"] = _t(g0[:, :EDGE_DIM])
+    o["NB_GX_W"] = _t(g0[:, EDGE_DIM:EDGE_DIM + NODE_DIM])
+    o["NB_GT_W"] = g0[:, EDGE_DIM + NODE_DIM]
+    o["NB_G1_B"] = sd[nb + ".gate.net.0.bias"]
+    o["NB_G1_G"] = sd[nb + ".gate.net.1.weight"]
+    o["NB_G1_BE"] = sd[nb + ".gate.net.1.bias"]
+    o["NB_G2_W"] = _t(sd[nb + ".gate.net.3.weight"])
+    o["NB_G2_B"] = sd[nb + ".gate.net.3.bias"]
+    o["NB_CEN_W"] = _t(sd[nb + ".centroid_lin.weight"])
+    o["NB_CEN_B"] = sd[nb + ".centroid_lin.bias"]
+    o["NB_LN_G"] = sd[nb + ".layer_norm.weight"]
+    o["NB_LN_BE"] = sd[nb + ".layer_norm.bias"]
+    o["NB_OUT_W"] = _t(sd[nb + ".out_transform.weight"])
+    o["NB_OUT_B"] = sd[nb + ".out_transform.bias"]
+    eb = f"{net_prefix}.edge_blocks.{i}"
+    _bond_ffn(sd, eb + ".bond_ffn_left", "EL", o, EDGE_DIM, NODE_DIM)
+    _bond_ffn(sd, eb + ".bond_ffn_right", "ER", o, EDGE_DIM, NODE_DIM)
+    o["EB_NFL_W"] = _t(sd[eb + ".node_ffn_left.weight"])
+    o["EB_NFL_B"] = sd[eb + ".node_ffn_left.bias"]
+    o["EB_NFR_W"] = _t(sd[eb + ".node_ffn_right.weight"])
+    o["EB_NFR_B"] = sd[eb + ".node_ffn_right.bias"]
+    o["EB_SELF_W"] = _t(sd[eb + ".self_ffn.weight"])
+    o["EB_SELF_B"] = sd[eb + ".self_ffn.bias"]
+    o["EB_LN_G"] = sd[eb + ".layer_norm.weight"]
+    o["EB_LN_BE"] = sd[eb + ".layer_norm.bias"]
+    o["EB_OUT_W"] = _t(sd[eb + ".out_transform.weight"])
+    o["EB_OUT_B"] = sd[eb + ".out_transform.bias"]
+    if update_pos:
+        pb = f"{net_prefix}.pos_blocks.{i}"
+        _mlp2(sd, pb + ".left_lin_edge", "PU_LL", o)
+        _mlp2(sd, pb + ".right_lin_edge", "PU_RL", o)
+        _bond_ffn(sd, pb + ".edge_lin", "PU", o, EDGE_DIM, EDGE_DIM)
+        o["PU_I2_W"] = o["PU_I2_W"].reshape(-1)      # Linear(256 -> 1): used as a dot product
+        o["PU_G2_W"] = o["PU_G2_W"].reshape(-1)      # Linear(32 -> 1)
+    return o
+
+
+def head_tensors(sd, kind, net_prefix, time_dim):
+    o = {"RBF_OFFSET": sd[f"{net_prefix}.distance_expansion.offset"],
+         "RBF_COEFF": sd[f"{net_prefix}.distance_expansion.coeff"]}
+    if kind == 0:
+        return o
+    tprefix = "time_emb.0" if kind == 1 else "time_emb"          # model.py:34-36 vs bond_predictor.py:31
+    if time_dim > 0:
+        o["TIME_OFFSET"] = sd[tprefix + ".offset"]
+        o["TIME_COEFF"] = sd[tprefix + ".coeff"]
+    o["NODE_EMB_W"] = _t(sd["node_embedder.weight"])             # [Kn][256 - time_dim]
+    o["EDGE_EMB_W"] = _t(sd["edge_embedder.weight"])             # [Ke | 2Kn][64 - time_dim]
+    if kind == 1:
+        _mlp2(sd, "node_decoder", "NDEC", o)
+        o["NDEC2_W"] = _pad_cols(o["NDEC2_W"], 32)
+        o["NDEC2_B"] = _pad_vec(o["NDEC2_B"], 32)
+        _mlp2(sd, "edge_decoder", "EDEC", o)
+        o["EDEC2_W"] = _pad_cols(o["EDEC2_W"], 32)
+        o["EDEC2_B"] = _pad_vec(o["EDEC2_B"], 32)
+    else:
+        # edge_decoder = MLP(64 + 256 -> 64 -> 64 -> K, num_layer=3)      bond_predictor.py:34
+        w0 = sd["edge_decoder.net.0.weight"]                     # [64][320]
+        o["EDEC1_W"] = _t(w0[:, :EDGE_DIM])
+        o["EDEC1N_W"] = _t(w0[:, EDGE_DIM:])
+        o["EDEC1_B"] = sd["edge_decoder.net.0.bias"]
+        o["EDEC1_G"] = sd["edge_decoder.net.1.weight"]
+        o["EDEC1_BE"] = sd["edge_decoder.net.1.bias"]
+        o["EDEC2_W"] = _t(sd["edge_decoder.net.3.weight"])
+        o["EDEC2_B"] = sd["edge_decoder.net.3.bias"]
+        o["EDEC3_G"] = sd["edge_decoder.net.4.weight"]
+        o["EDEC3_BE"] = sd["edge_decoder.net.4.bias"]
+        o["EDEC3_W"] = _pad_cols(_t(sd["edge_decoder.net.6.weight"]), 32)
+        o["EDEC3_B"] = _pad_vec(sd["edge_decoder.net.6.bias"], 32)
+    return o
+
+
+def pack_network(sd, *, kind, net_prefix, num_blocks, update_pos, time_dim=0):
+    """Returns (blob fp32 1-D CPU tensor, head_off list[int], block_off list[list[int]]); -1 = absent."""
+    if num_blocks > MAX_BLOCKS:
+        raise ValueError(f"num_blocks {num_blocks} > {MAX_BLOCKS}")
+    chunks, cursor = [], 0
+
+    def put(tensor):
+        nonlocal cursor
+        flat = tensor.detach().to(torch.float32).reshape(-1).cpu()
+        off = cursor
+        pad = (-flat.numel()) % _ALIGN
+        chunks.append(flat)
+        if pad:
+            chunks.append(torch.zeros(pad, dtype=torch.float32))
+        cursor += flat.numel() + pad
+        return off
+
+    head = head_tensors(sd, kind, net_prefix, time_dim)
+    head_off = [put(head[s]) if s in head else -1 for s in HEAD_SLOTS]
+    block_off = []
+    for i in range(num_blocks):
+        bt = block_tensors(sd, net_prefix, i, update_pos)
+        unknown = set(bt) - set(BLOCK_SLOTS)
+        if unknown:
+            raise RuntimeError(f"packer produced unknown slots {sorted(unknown)}")
+        block_off.append([put(bt[s]) if s in bt else -1 for s in BLOCK_SLOTS])
+    return torch.cat(chunks), head_off, block_off

@@ -1,0 +1,168 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI (ctypes), against the oracle and the reference goldens.
+
+Bar: max|delta| <= 1e-4 * max|ref| per output tensor against the fp32 reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+from tests.helpers import batch_inputs, doubled, oracle_moldiff, to_dev
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def gpu_models(seeded_models, dev):
+    import copy
+    md, bp = seeded_models
+    return copy.deepcopy(md).to(dev).eval(), copy.deepcopy(bp).to(dev).eval()
+
+
+def cuda_moldiff(model, inp, dev):
+    d = to_dev(inp, dev)
+    ei, be, he = doubled(d)
+    with torch.no_grad():
+        out = model(d["h_node"], d["pos"], d["batch_node"], he, ei, be, d["t"])
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+def test_library_loaded_and_counts_launches(gpu_models, dev):
+    from moldiff_b200 import engine
+    before = engine.launch_count()
+    cuda_moldiff(gpu_models[0], batch_inputs(B=2), dev)
+    assert engine.launch_count() - before == 2 + 1 + 3 * 6 + 1   # init x2, pre(0), 3 per block, edge decode
+
+
+@pytest.mark.parametrize("name", ["B4_mixed_t", "B4_pos3", "B32_t500"])
+def test_moldiff_forward_vs_reference_goldens(name, golden, gpu_models, dev):
+    case = golden["moldiff_forward"][name]
+    out = cuda_moldiff(gpu_models[0], batch_inputs(**case["args"]), dev)
+    for k, ref in case["out"].items():
+        assert torch.isfinite(out[k]).all(), k
+        err = R.rel_err(out[k], ref)
+        assert err < TOL, (name, k, err)
+
+
+@pytest.mark.parametrize("B,t_values,pos_scale,seed", [
+    (1, (0,), 1.0, 3), (5, (999,), 1.0, 4), (7, (1, 500, 998), 3.0, 5), (64, (250, 750), 1.0, 6)])
+def test_moldiff_forward_vs_oracle(B, t_values, pos_scale, seed, seeded_models, gpu_models, dev):
+    inp = batch_inputs(B=B, seed_graph=seed, seed_inputs=seed + 100, t_values=t_values, pos_scale=pos_scale)
+    ref = oracle_moldiff(seeded_models[0].state_dict(), inp)
+    out = cuda_moldiff(gpu_models[0], inp, dev)
+    for k in ref:
+        err = R.rel_err(out[k], ref[k])
+        assert err < TOL, (k, err)
+
+
+def test_qm9_sized_dense_batch(seeded_models, gpu_models, dev):
+    """BASELINE config 5 shape (every molecule 29 atoms) at a size the oracle finishes in seconds."""
+    inp = batch_inputs(B=24, max_size=29, t_values=(300, 900))
+    ref = oracle_moldiff(seeded_models[0].state_dict(), inp)
+    out = cuda_moldiff(gpu_models[0], inp, dev)
+    for k in ref:
+        assert R.rel_err(out[k], ref[k]) < TOL, k
+
+
+def test_soft_inputs_continuous_space(seeded_models, gpu_models, dev):
+    """h_node_pert / h_edge_pert need not be one-hot (categorical_space == 'continuous', model.py:124-125)."""
+    inp = batch_inputs(B=3, t_values=(400,))
+    g = torch.Generator().manual_seed(5)
+    inp["h_node"] = torch.randn(inp["h_node"].shape, generator=g)
+    inp["h_half"] = torch.randn(inp["h_half"].shape, generator=g)
+    ref = oracle_moldiff(seeded_models[0].state_dict(), inp)
+    out = cuda_moldiff(gpu_models[0], inp, dev)
+    for k in ref:
+        assert R.rel_err(out[k], ref[k]) < TOL, k
+
+
+def test_node_edge_net_api_arbitrary_edge_order(seeded_models, gpu_models, dev):
+    """NodeEdgeNet.forward(h_node, pos, h_edge, edge_index, node_time, edge_time) with a SHUFFLED edge list
+    (the op must accept any edge_index, graph.py:348): results must come back in the caller's edge order."""
+    inp = batch_inputs(B=3, t_values=(100, 600, 900))
+    ei, be, _ = doubled(inp)
+    g = torch.Generator().manual_seed(9)
+    shuffle = torch.randperm(ei.shape[1], generator=g)
+    ei, be = ei[:, shuffle], be[shuffle]
+    N, E = len(inp["batch_node"]), ei.shape[1]
+    h_node, h_edge = torch.randn(N, 256, generator=g), torch.randn(E, 64, generator=g)
+    nt = (inp["t"][inp["batch_node"]].float() / 1000).unsqueeze(-1)
+    et = (inp["t"][be].float() / 1000).unsqueeze(-1)
+    sd = {"denoiser." + k: v.cpu() for k, v in gpu_models[0].denoiser.state_dict().items()}
+    with torch.no_grad():
+        ref = R.node_edge_net(sd, "denoiser", h_node, inp["pos"], h_edge, ei, nt, et, num_blocks=6, cutoff=15.0)
+        out = gpu_models[0].denoiser(h_node.to(dev), inp["pos"].to(dev), h_edge.to(dev), ei.to(dev), nt.to(dev), et.to(dev))
+    for nm, a, b in zip(("h_node", "pos", "h_edge"), out, ref):
+        assert R.rel_err(a.cpu(), b) < TOL, nm
+
+
+def test_bondpred_forward(golden, seeded_models, gpu_models, dev):
+    for name, case in golden["bondpred"].items():
+        inp = batch_inputs(**case["args"])
+        d = to_dev(inp, dev)
+        ei, be, _ = doubled(d)
+        with torch.no_grad():
+            logits = gpu_models[1](d["h_node"], d["pos"], d["batch_node"], ei, be, d["t"])
+        err = R.rel_err(logits.cpu(), case["out"]["logits"])
+        assert err < TOL, (name, err)
+
+
+def test_sample50_teacher_forced_steps(golden, dev):
+    """Teacher-forced per-step parity on the reference's own 50-step trajectory (SURVEY.md 8c protocol 4)."""
+    from moldiff_b200 import MolDiff
+    from moldiff_b200.config import builtin_config
+    cfg = builtin_config("train/train_MolDiff_simple.yml").model
+    cfg.diff.num_timesteps = 50
+    torch.manual_seed(0)
+    model = MolDiff(cfg, 8, 6).to(dev).eval()
+    np.random.seed(2023)
+    ph = R.make_data_placeholder(3)
+    ei = torch.cat([ph["halfedge_index"], ph["halfedge_index"].flip(0)], dim=1).to(dev)
+    be = torch.cat([ph["batch_halfedge"], ph["batch_halfedge"]], dim=0).to(dev)
+    for i, st in golden["sample50"]["steps"].items():
+        t = torch.full((3,), st["step"], dtype=torch.long, device=dev)
+        with torch.no_grad():
+            pr = model(st["h_node"].to(dev), st["pos"].to(dev), ph["batch_node"].to(dev),
+                       torch.cat([st["h_half"]] * 2, 0).to(dev), ei, be, t)
+        for k, ref in st["preds"].items():
+            err = R.rel_err(pr[k].cpu(), ref)
+            assert err < TOL, (i, k, err)
+
+
+def test_free_running_sample_is_finite_and_plausible(dev):
+    """Distributional smoke (protocol 5): a free-running 50-step sample stays finite; types are valid one-hots."""
+    from moldiff_b200 import MolDiff
+    from moldiff_b200.config import builtin_config
+    cfg = builtin_config("train/train_MolDiff_simple.yml").model
+    cfg.diff.num_timesteps = 50
+    torch.manual_seed(0)
+    model = MolDiff(cfg, 8, 6).to(dev).eval()
+    np.random.seed(2023)
+    ph = {k: v.to(dev) for k, v in R.make_data_placeholder(8).items()}
+    torch.manual_seed(2023)
+    out = model.sample(8, ph["batch_node"], ph["halfedge_index"], ph["batch_halfedge"])
+    node_traj, pos_traj, half_traj = out["traj"]
+    assert node_traj.shape[0] == 51 and torch.isfinite(pos_traj).all()
+    assert torch.all(node_traj[-1].sum(-1) == 1) and torch.all(half_traj[-1].sum(-1) == 1)
+    for x in out["pred"]:
+        assert torch.isfinite(x).all()
+
+
+def test_rejects_cpu_tensors_and_bad_shapes(gpu_models, dev):
+    from moldiff_b200.engine import MoldiffB200Error
+    inp = batch_inputs(B=2)
+    ei, be, he = doubled(inp)
+    with pytest.raises(MoldiffB200Error):
+        gpu_models[0](inp["h_node"], inp["pos"], inp["batch_node"], he, ei, be, inp["t"])   # CPU tensors
+    d = to_dev(inp, dev)
+    ei, be, he = doubled(d)
+    with pytest.raises(MoldiffB200Error):
+        gpu_models[0](d["h_node"][:, :5], d["pos"], d["batch_node"], he, ei, be, d["t"])
