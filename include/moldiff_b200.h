@@ -162,6 +162,26 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
                           const float* d_logits, float* d_pos,
                           float* workspace, size_t workspace_bytes, void* stream);
 
+/* Kernel classes, for the per-kernel device timing bench.py reports (order is the ABI). */
+#define MDB_KERNEL_CLASSES(X)                                                                      \
+  X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
+  X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)
+
+enum mdb_kernel_class {
+#define MDB_X(name) MDB_K_##name,
+  MDB_KERNEL_CLASSES(MDB_X)
+#undef MDB_X
+  MDB_NUM_KERNEL_CLASSES
+};
+
+/* Profiling: between begin and end every kernel launch of this library is bracketed by CUDA events on
+ * its own stream; end synchronises those events and returns summed milliseconds / launch counts per
+ * kernel class (arrays of MDB_NUM_KERNEL_CLASSES).  Not for use inside a timed region. */
+void mdb_profile_begin(void);
+int mdb_profile_end(double* ms_per_class, int64_t* launches_per_class);
+const char* mdb_kernel_class_name(int cls);
+int mdb_num_kernel_classes(void);
+
 /* Diagnostics. */
 const char* mdb_last_error(void);
 int mdb_version(void);

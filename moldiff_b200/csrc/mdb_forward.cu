@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/moldiff_b200.h"
 #include "tile_engine.cuh"
 
@@ -34,7 +36,8 @@ struct Tables {
   float *x, *agg, *hn, *gx, *cen;       // [N][256]
   float *nll, *nlr;                     // [N][128]   bond_ffn_{left,right}.node_linear(h_node)
   float *gnl, *gnr;                     // [N][32]    bond_ffn gate first layer, node + time + bias part
-  float *fl, *fr, *lf, *rf, *dect;      // [N][64]
+  float *fl, *fr;                       // [2 parities][N][64]  node_ffn_{left,right}(h_node)
+  float *lf, *rf, *dect;                // [N][64]
   float *slsr;                          // [2 parities][2 (SL,SR)][N][64]
   float *pos0, *pos1;                   // [N][3]
   float *tn;                            // [N]
@@ -256,15 +259,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_kernel(const NodeArgs a) {
       {
         float acc[8][1];
         tile_gemm<D, 32>(acc, X, D, side ? W_(ER_GN_W) : W_(EL_GN_W), Ws);
-        add_rowvec<32>(acc, side ? W_(ER_G1_B) : W_(EL_G1_B), lane);
-        add_scaled_rowvec<32>(acc, side ? W_(ER_GT_W) : W_(EL_GT_W), tns + warp * 8, lane);
+        add_rowvec<32>(acc, side ? W_(ER_G1_B) : W_(EL_G1_B), lane);   // the time column uses the EDGE time: added per edge
         store_table<32>(acc, side ? tb.gnr : tb.gnl, row0, a.n_nodes, warp, lane);
       }
       {
         float acc[8][2];
         tile_gemm<D, C>(acc, X, D, side ? W_(EB_NFR_W) : W_(EB_NFL_W), Ws);
         add_rowvec<C>(acc, side ? W_(EB_NFR_B) : W_(EB_NFL_B), lane);
-        store_table<C>(acc, side ? tb.fr : tb.fl, row0, a.n_nodes, warp, lane);
+        // parity-buffered: edge_kernel_d(i) still reads block i's values after this kernel wrote block i+1's
+        store_table<C>(acc, (side ? tb.fr : tb.fl) + (size_t)a.par_next * a.n_nodes * C, row0, a.n_nodes, warp, lane);
       }
     }
     // clear the SL/SR accumulators the next edge_kernel_b will add into
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_b(const EdgeArgs a) {
       float g1[8][1];
       tile_gemm<C, 32>(g1, Es, C, side ? W_(ER_GB_W) : W_(EL_GB_W), Ws);        // gate.net.0 bond columns
       gather_rows<32, false>(g1, side ? tb.gnr : tb.gnl, nw, lane);
+      add_scaled_rowvec<32>(g1, side ? W_(ER_GT_W) : W_(EL_GT_W), tes + warp * 8, lane);
       layernorm_rows<32, true>(g1, side ? W_(ER_G1_G) : W_(EL_G1_G), side ? W_(ER_G1_BE) : W_(EL_G1_BE), lane);
       store_smem<32>(g1, Bf, 32, warp, lane);
       float g2[8][2];
@@ -488,8 +492,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_d(const EdgeArgs a) {
     add_rowvec<C>(acc, W_(EB_SELF_B), lane);
     gather_rows<C, false>(acc, sl, lw, lane);       // scatter_sum(msg_left, right)[left]
     gather_rows<C, false>(acc, sr, rw, lane);       // scatter_sum(msg_right, left)[right]
-    gather_rows<C, false>(acc, tb.fl, lw, lane);    // node_ffn_left(h_node[left])
-    gather_rows<C, false>(acc, tb.fr, rw, lane);    // node_ffn_right(h_node[right])
+    gather_rows<C, false>(acc, tb.fl + (size_t)a.par * a.n_nodes * C, lw, lane);   // node_ffn_left(h_node[left])
+    gather_rows<C, false>(acc, tb.fr + (size_t)a.par * a.n_nodes * C, rw, lane);   // node_ffn_right(h_node[right])
     layernorm_rows<C, true>(acc, W_(EB_LN_G), W_(EB_LN_BE), lane);
     store_smem<C>(acc, A, C, warp, lane);
     tile_gemm<C, C>(acc, A, C, W_(EB_OUT_W), Ws);
@@ -639,6 +643,23 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 // ------------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
 int64_t g_launches = 0;
+bool g_profiling = false;
+struct ProfRec { int cls; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof;
+
+// Every launch goes through LAUNCH so that it is counted and, when profiling, timed on its own stream.
+#define LAUNCH(kcls_, st, ...)                                             \
+  do {                                                                    \
+    ProfRec pr_;                                                          \
+    if (g_profiling) {                                                    \
+      pr_.cls = (kcls_);                                                  \
+      cudaEventCreate(&pr_.a); cudaEventCreate(&pr_.b);                   \
+      cudaEventRecord(pr_.a, (st));                                       \
+    }                                                                     \
+    __VA_ARGS__;                                                          \
+    ++g_launches;                                                         \
+    if (g_profiling) { cudaEventRecord(pr_.b, (st)); g_prof.push_back(pr_); } \
+  } while (0)
 
 int fail(int code, const char* fmt, const char* extra = "") {
   snprintf(g_err, sizeof(g_err), fmt, extra);
@@ -659,7 +680,7 @@ size_t carve(Tables& tb, float* base, int64_t N, int64_t E) {
   tb.x = take(N * D); tb.agg = take(N * D); tb.hn = take(N * D); tb.gx = take(N * D); tb.cen = take(N * D);
   tb.nll = take(N * 128); tb.nlr = take(N * 128);
   tb.gnl = take(N * 32); tb.gnr = take(N * 32);
-  tb.fl = take(N * C); tb.fr = take(N * C); tb.lf = take(N * C); tb.rf = take(N * C); tb.dect = take(N * C);
+  tb.fl = take(2 * N * C); tb.fr = take(2 * N * C); tb.lf = take(N * C); tb.rf = take(N * C); tb.dect = take(N * C);
   tb.slsr = take(4 * N * C);
   tb.pos0 = take(N * 3); tb.pos1 = take(N * 3);
   tb.tn = take(N);
@@ -720,15 +741,15 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
   const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
 
-  node_init_kernel<<<N, D, 0, st>>>(net->kind, N, net->num_node_types, net->time_dim, net->num_timesteps,
-                                    net->blob, head, in.h_node, in.batch_node, in.t, in.node_time, tb.x, tb.tn);
-  ++g_launches;
+  LAUNCH(MDB_K_node_init, st,
+         (node_init_kernel<<<N, D, 0, st>>>(net->kind, N, net->num_node_types, net->time_dim, net->num_timesteps,
+                                            net->blob, head, in.h_node, in.batch_node, in.t, in.node_time, tb.x, tb.tn)));
   if (E > 0) {
-    edge_init_kernel<<<(E + 3) / 4, 256, 0, st>>>(net->kind, E, net->num_node_types, net->num_edge_types,
-                                                  net->time_dim, net->num_timesteps, net->blob, head,
-                                                  in.h_edge, in.h_node, in.batch_edge, in.t, in.edge_time,
-                                                  plan->left, plan->right, plan->perm, tb.hedge, tb.te);
-    ++g_launches;
+    LAUNCH(MDB_K_edge_init, st,
+           (edge_init_kernel<<<(E + 3) / 4, 256, 0, st>>>(net->kind, E, net->num_node_types, net->num_edge_types,
+                                                          net->time_dim, net->num_timesteps, net->blob, head,
+                                                          in.h_edge, in.h_node, in.batch_edge, in.t, in.edge_time,
+                                                          plan->left, plan->right, plan->perm, tb.hedge, tb.te)));
   }
   CUDA_TRY(cudaMemsetAsync(tb.agg, 0, (size_t)N * D * sizeof(float), st));
   CUDA_TRY(cudaMemcpyAsync(tb.pos0, in.pos, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -742,8 +763,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   // pre(0)
   fill_blk(na.pre, net, 0);
   na.do_mid = 0; na.do_pre = 1; na.do_dec = 0; na.par_next = 0; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
-  node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na);
-  ++g_launches;
+  LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
 
   EdgeArgs ea;
   memset(&ea, 0, sizeof(ea));
@@ -754,28 +774,26 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   for (int i = 0; i < L; ++i) {
     fill_blk(ea.off, net, i);
     ea.par = i & 1; ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
-    if (E > 0) { edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea); ++g_launches; }
+    if (E > 0) LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
     fill_blk(na.mid, net, i);
     na.do_mid = 1; na.do_pre = (i + 1 < L); na.do_dec = (i + 1 == L) && net->kind != 0;
     if (na.do_pre) fill_blk(na.pre, net, i + 1);
     na.par_next = (i + 1) & 1; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
-    node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na);
-    ++g_launches;
-    if (E > 0) { edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea); ++g_launches; }
+    LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
+    if (E > 0) LAUNCH(MDB_K_edge_d, st, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea)));
     if (net->update_pos) { const float* t_ = pos_cur; pos_cur = pos_nxt; pos_nxt = const_cast<float*>(t_); }
   }
 
   if (net->kind == 0) {
     CUDA_TRY(cudaMemcpyAsync(in.out_node, tb.x, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (E > 0) { edge_unsort_kernel<<<(E + 3) / 4, 256, 0, st>>>(E, plan->perm, tb.hedge, in.out_edge); ++g_launches; }
+    if (E > 0) LAUNCH(MDB_K_edge_unsort, st, (edge_unsort_kernel<<<(E + 3) / 4, 256, 0, st>>>(E, plan->perm, tb.hedge, in.out_edge)));
   } else if (plan->n_half > 0) {
     DecArgs da;
     memset(&da, 0, sizeof(da));
     da.blob = net->blob; da.head = head; da.tb = tb; da.left = plan->left; da.right = plan->right;
     da.inv = plan->inv; da.n_half = plan->n_half; da.kind = net->kind; da.ke = net->num_edge_types;
     da.out = in.out_edge;
-    edge_decode_kernel<<<(plan->n_half + TM - 1) / TM, NTHREADS, SMEM_DEC, st>>>(da);
-    ++g_launches;
+    LAUNCH(MDB_K_edge_decode, st, (edge_decode_kernel<<<(plan->n_half + TM - 1) / TM, NTHREADS, SMEM_DEC, st>>>(da)));
   }
   if (in.out_pos)
     CUDA_TRY(cudaMemcpyAsync(in.out_pos, pos_cur, (size_t)N * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -834,6 +852,37 @@ int mdb_bondpred_backward(const mdb_net_desc*, const mdb_plan*, const float*, co
                           const int64_t*, const int64_t*, const float*, float*, float*, size_t, void*) {
   return fail(MDB_EINVAL, "mdb_bondpred_backward: backward kernels not built yet%s");
 }
+
+void mdb_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_profiling = true;
+}
+
+int mdb_profile_end(double* ms_per_class, int64_t* launches_per_class) {
+  g_profiling = false;
+  for (int i = 0; i < MDB_NUM_KERNEL_CLASSES; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+  for (auto& r : g_prof) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_class[r.cls] += ms;
+    launches_per_class[r.cls] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return MDB_OK;
+}
+
+const char* mdb_kernel_class_name(int cls) {
+  static const char* names[] = {
+#define MDB_X(name) #name,
+      MDB_KERNEL_CLASSES(MDB_X)
+#undef MDB_X
+  };
+  return (cls >= 0 && cls < MDB_NUM_KERNEL_CLASSES) ? names[cls] : "?";
+}
+int mdb_num_kernel_classes(void) { return MDB_NUM_KERNEL_CLASSES; }
 
 const char* mdb_last_error(void) { return g_err; }
 int mdb_version(void) { return 1; }

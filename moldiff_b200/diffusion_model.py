@@ -204,64 +204,81 @@ class MolDiff(nn.Module, _PackedMixin):
         return sign * grad * gui_scale
 
     @torch.no_grad()
+    def sample_begin(self, n_graphs, batch_node, halfedge_index, batch_halfedge):
+        """Draw x_T and build the per-batch constants of the sampling loop (model.py:238-270).  Returns the
+        mutable sampler state used by `sample_step` (and by bench.py, whose timed "step" is one loop body)."""
+        n_nodes, n_half = len(batch_node), len(batch_halfedge)
+        discrete = self.categorical_space == "discrete"
+        node_init = self.node_transition.sample_init(n_nodes)
+        pos = self.pos_transition.sample_init([n_nodes, 3])
+        half_init = self.edge_transition.sample_init(n_half)
+        st = {"n_graphs": n_graphs, "batch_node": batch_node, "batch_halfedge": batch_halfedge, "pos": pos,
+              "edge_index": torch.cat([halfedge_index, halfedge_index.flip(0)], dim=1),
+              "batch_edge": torch.cat([batch_halfedge, batch_halfedge], dim=0)}
+        if discrete:
+            _, st["h_node"], st["log_node"] = node_init
+            _, st["h_half"], st["log_half"] = half_init
+        else:
+            st["h_node"], st["h_half"] = node_init, half_init
+        return st
+
+    @torch.no_grad()
+    def sample_step(self, st, step, bond_predictor=None, guidance=None):
+        """One body of the reverse loop at timestep `step` (model.py:272-372): denoise, sample x_{t-1} from the
+        posteriors, add the guidance drift.  Mutates `st`; returns the step's predictions."""
+        device = st["pos"].device
+        discrete = self.categorical_space == "discrete"
+        batch_node, batch_halfedge = st["batch_node"], st["batch_halfedge"]
+        h_node, pos, h_half = st["h_node"], st["pos"], st["h_half"]
+        time_step = torch.full((st["n_graphs"],), step, dtype=torch.long, device=device)
+        preds = self(h_node, pos, batch_node, torch.cat([h_half, h_half], dim=0), st["edge_index"],
+                     st["batch_edge"], time_step)
+        pred_node, pred_pos, pred_half = preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]
+
+        pos_prev = self.pos_transition.get_prev_from_recon(x_t=pos, x_recon=pred_pos, t=time_step, batch=batch_node)
+        half_type_prev = None
+        if discrete:
+            st["log_node"] = self.node_transition.q_v_posterior(F.log_softmax(pred_node, dim=-1), st["log_node"],
+                                                                time_step, batch_node, v0_prob=True)
+            h_node_prev = self.node_transition.onehot_encode(gumbel_argmax(st["log_node"]))
+            st["log_half"] = self.edge_transition.q_v_posterior(F.log_softmax(pred_half, dim=-1), st["log_half"],
+                                                                time_step, batch_halfedge, v0_prob=True)
+            half_type_prev = gumbel_argmax(st["log_half"])
+            h_half_prev = self.edge_transition.onehot_encode(half_type_prev)
+        else:
+            h_node_prev = self.node_transition.get_prev_from_recon(x_t=h_node, x_recon=pred_node, t=time_step,
+                                                                   batch=batch_node)
+            h_half_prev = self.edge_transition.get_prev_from_recon(x_t=h_half, x_recon=pred_half, t=time_step,
+                                                                   batch=batch_halfedge)
+        if guidance is not None:
+            gui_type, gui_scale = guidance
+            if gui_scale > 0:
+                pos_prev = pos_prev + self._guidance_delta(
+                    bond_predictor, gui_type, gui_scale, h_node, pos, batch_node, st["edge_index"], st["batch_edge"],
+                    time_step, half_type_prev, st["log_half"] if discrete else None)
+        st["h_node"], st["pos"], st["h_half"] = h_node_prev, pos_prev, h_half_prev
+        return preds
+
+    @torch.no_grad()
     def sample(self, n_graphs, batch_node, halfedge_index, batch_halfedge, bond_predictor=None, guidance=None,
                progress=False):
         """T-step ancestral sampling (model.py:236-378).  Returns {'pred': [node, pos, halfedge] of the
         last step, 'traj': [node_traj, pos_traj, halfedge_traj]} exactly like the reference."""
         device = batch_node.device
-        n_nodes, n_half = len(batch_node), len(batch_halfedge)
         T = self.num_timesteps
-        discrete = self.categorical_space == "discrete"
-
-        node_init = self.node_transition.sample_init(n_nodes)
-        pos = self.pos_transition.sample_init([n_nodes, 3])
-        half_init = self.edge_transition.sample_init(n_half)
-        if discrete:
-            _, h_node, log_node = node_init
-            _, h_half, log_half = half_init
-        else:
-            h_node, h_half = node_init, half_init
-
-        node_traj = torch.zeros([T + 1, n_nodes, h_node.shape[-1]], dtype=h_node.dtype, device=device)
-        pos_traj = torch.zeros([T + 1, n_nodes, 3], dtype=pos.dtype, device=device)
-        half_traj = torch.zeros([T + 1, n_half, h_half.shape[-1]], dtype=h_half.dtype, device=device)
-        node_traj[0], pos_traj[0], half_traj[0] = h_node, pos, h_half
-
-        edge_index = torch.cat([halfedge_index, halfedge_index.flip(0)], dim=1)
-        batch_edge = torch.cat([batch_halfedge, batch_halfedge], dim=0)
+        st = self.sample_begin(n_graphs, batch_node, halfedge_index, batch_halfedge)
+        n_nodes, n_half = len(batch_node), len(batch_halfedge)
+        node_traj = torch.zeros([T + 1, n_nodes, st["h_node"].shape[-1]], dtype=st["h_node"].dtype, device=device)
+        pos_traj = torch.zeros([T + 1, n_nodes, 3], dtype=st["pos"].dtype, device=device)
+        half_traj = torch.zeros([T + 1, n_half, st["h_half"].shape[-1]], dtype=st["h_half"].dtype, device=device)
+        node_traj[0], pos_traj[0], half_traj[0] = st["h_node"], st["pos"], st["h_half"]
         steps = range(T - 1, -1, -1)
         if progress:
             from tqdm import tqdm
             steps = tqdm(steps, total=T)
-        pred_node = pred_pos = pred_half = None
+        preds = None
         for i, step in enumerate(steps):
-            time_step = torch.full((n_graphs,), step, dtype=torch.long, device=device)
-            preds = self(h_node, pos, batch_node, torch.cat([h_half, h_half], dim=0), edge_index, batch_edge, time_step)
-            pred_node, pred_pos, pred_half = preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]
-
-            pos_prev = self.pos_transition.get_prev_from_recon(x_t=pos, x_recon=pred_pos, t=time_step, batch=batch_node)
-            half_type_prev = None
-            if discrete:
-                log_node = self.node_transition.q_v_posterior(F.log_softmax(pred_node, dim=-1), log_node,
-                                                              time_step, batch_node, v0_prob=True)
-                h_node_prev = self.node_transition.onehot_encode(gumbel_argmax(log_node))
-                log_half = self.edge_transition.q_v_posterior(F.log_softmax(pred_half, dim=-1), log_half,
-                                                              time_step, batch_halfedge, v0_prob=True)
-                half_type_prev = gumbel_argmax(log_half)
-                h_half_prev = self.edge_transition.onehot_encode(half_type_prev)
-            else:
-                h_node_prev = self.node_transition.get_prev_from_recon(x_t=h_node, x_recon=pred_node, t=time_step,
-                                                                       batch=batch_node)
-                h_half_prev = self.edge_transition.get_prev_from_recon(x_t=h_half, x_recon=pred_half, t=time_step,
-                                                                       batch=batch_halfedge)
-            if guidance is not None:
-                gui_type, gui_scale = guidance
-                if gui_scale > 0:
-                    pos_prev = pos_prev + self._guidance_delta(
-                        bond_predictor, gui_type, gui_scale, h_node, pos, batch_node, edge_index, batch_edge,
-                        time_step, half_type_prev, log_half if discrete else None)
-
-            node_traj[i + 1], pos_traj[i + 1], half_traj[i + 1] = h_node_prev, pos_prev, h_half_prev
-            h_node, pos, h_half = h_node_prev, pos_prev, h_half_prev
-
-        return {"pred": [pred_node, pred_pos, pred_half], "traj": [node_traj, pos_traj, half_traj]}
+            preds = self.sample_step(st, step, bond_predictor=bond_predictor, guidance=guidance)
+            node_traj[i + 1], pos_traj[i + 1], half_traj[i + 1] = st["h_node"], st["pos"], st["h_half"]
+        return {"pred": [preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]],
+                "traj": [node_traj, pos_traj, half_traj]}

@@ -82,6 +82,12 @@ def load_library():
         lib.mdb_bondpred_forward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 6 + [i32, vp, sz, vp]
         lib.mdb_bondpred_backward.restype = C.c_int
         lib.mdb_bondpred_backward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 8 + [sz, vp]
+        lib.mdb_profile_begin.restype = None
+        lib.mdb_profile_end.restype = C.c_int
+        lib.mdb_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        lib.mdb_kernel_class_name.restype = C.c_char_p
+        lib.mdb_kernel_class_name.argtypes = [C.c_int]
+        lib.mdb_num_kernel_classes.restype = C.c_int
         lib.mdb_last_error.restype = C.c_char_p
         lib.mdb_version.restype = C.c_int
         lib.mdb_launch_count.restype = i64
@@ -91,6 +97,37 @@ def load_library():
 
 def launch_count():
     return int(load_library().mdb_launch_count())
+
+
+# As-written (reference) GEMM FLOPs per directed edge executed inside each edge kernel class per launch
+# (SURVEY.md 8d / BASELINE.md: edge_emb 10 240 + NodeBlock edge part 2*(64*256*2 + 256*256*3 + ...) etc.).
+KERNEL_LOGICAL_FLOP_PER_EDGE = {
+    # edge_embs (80->64) + NodeBlock per-edge Linears as written (edge_net 64->256->256, msg 256->256,
+    # gate 321->256->256) + two BondFFNs as written (bond 64->128, node 256->128, inter 128->128->64, gate 321->32->64)
+    "edge_b": 2.0 * (80 * 64 + 64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256
+                     + 2 * (64 * 128 + 256 * 128 + 128 * 128 + 128 * 64 + 321 * 32 + 32 * 64)),
+    # EdgeBlock tail (node_ffn L/R 256->64, self 64->64, out 64->64) + PosUpdate as written
+    "edge_d": 2.0 * (2 * 256 * 64 + 64 * 64 + 64 * 64
+                     + 2 * (256 * 64 + 64 * 64) + 64 * 256 + 64 * 256 + 256 * 256 + 256 + 129 * 32 + 32),
+}
+
+
+def profile_kernels(fn, reps=1):
+    """Run fn() `reps` times with per-kernel CUDA-event timing enabled; returns {class: {ms_total, launches}}."""
+    lib = load_library()
+    n = lib.mdb_num_kernel_classes()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    torch.cuda.synchronize()
+    lib.mdb_profile_begin()
+    try:
+        for _ in range(reps):
+            fn()
+    finally:
+        rc = lib.mdb_profile_end(ms, cnt)
+    _check(rc, "mdb_profile_end")
+    return {lib.mdb_kernel_class_name(i).decode(): {"ms_total": float(ms[i]), "launches": int(cnt[i])}
+            for i in range(n) if cnt[i] > 0}
 
 
 def _check(rc, what):
