@@ -66,7 +66,15 @@ extern "C" {
   X(PU_LL1_W) X(PU_LL1_B) X(PU_LL1_G) X(PU_LL1_BE) X(PU_LL2_W) X(PU_LL2_B)                         \
   X(PU_RL1_W) X(PU_RL1_B) X(PU_RL1_G) X(PU_RL1_BE) X(PU_RL2_W) X(PU_RL2_B)                         \
   X(PU_PB_W) X(PU_PN_W) X(PU_I1_W) X(PU_I1_B) X(PU_I1_G) X(PU_I1_BE) X(PU_I2_W) X(PU_I2_B)         \
-  X(PU_GB_W) X(PU_GN_W) X(PU_GT_W) X(PU_G1_B) X(PU_G1_G) X(PU_G1_BE) X(PU_G2_W) X(PU_G2_B)
+  X(PU_GB_W) X(PU_GN_W) X(PU_GT_W) X(PU_G1_B) X(PU_G1_G) X(PU_G1_BE) X(PU_G2_W) X(PU_G2_B)         \
+  /* input-gradient backward (bond predictor only): the same Linears stored [out][in], i.e. [K][N]  */  \
+  /* for dX = dY * W; EE split into its h_edge (64) and rbf (16, padded to 32) columns              */  \
+  X(T_EEH) X(T_EEG)                                                                                \
+  X(T_NB_NN1) X(T_NB_NN2) X(T_NB_EN1) X(T_NB_EN2) X(T_NB_MSG) X(T_NB_GE) X(T_NB_GX) X(T_NB_G2)     \
+  X(T_NB_CEN) X(T_NB_OUT)                                                                          \
+  X(T_EL_BL) X(T_EL_NL) X(T_EL_I1) X(T_EL_I2) X(T_EL_GB) X(T_EL_GN) X(T_EL_G2)                     \
+  X(T_ER_BL) X(T_ER_NL) X(T_ER_I1) X(T_ER_I2) X(T_ER_GB) X(T_ER_GN) X(T_ER_G2)                     \
+  X(T_EB_NFL) X(T_EB_NFR) X(T_EB_SELF) X(T_EB_OUT)
 
 enum mdb_block_slot {
 #define MDB_X(name) MDB_S_##name,
@@ -84,7 +92,8 @@ enum mdb_block_slot {
   X(NDEC1_W) X(NDEC1_B) X(NDEC1_G) X(NDEC1_BE) X(NDEC2_W) X(NDEC2_B) /* node_decoder, out padded to 32 */ \
   X(EDEC1_W) X(EDEC1_B) X(EDEC1_G) X(EDEC1_BE) X(EDEC2_W) X(EDEC2_B) /* edge_decoder, out padded to 32 */ \
   X(EDEC1N_W)                          /* bond predictor: node half of edge_decoder.net.0 [256][64] */ \
-  X(EDEC3_G) X(EDEC3_BE) X(EDEC3_W) X(EDEC3_B) /* bond predictor: third layer (LN + Linear, out padded to 32) */
+  X(EDEC3_G) X(EDEC3_BE) X(EDEC3_W) X(EDEC3_B) /* bond predictor: third layer (LN + Linear, out padded to 32) */ \
+  X(T_EDEC1) X(T_EDEC1N) X(T_EDEC2) X(T_EDEC3) /* bond predictor backward: edge_decoder Linears stored [out][in] */
 
 enum mdb_head_slot {
 #define MDB_X(name) MDB_H_##name,

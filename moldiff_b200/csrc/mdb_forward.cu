@@ -136,7 +136,10 @@ struct NodeArgs {
   int do_mid, do_pre, do_dec;   // phases
   int update_pos;
   int kind, kn;
-  int par_next;                 // parity of the SL/SR buffer to clear for the `pre` block
+  float* sl_next;               // [2 (SL,SR)][N][64] accumulators to clear for the `pre` block
+  float *fl_next, *fr_next;     // [N][64] node_ffn_{left,right} outputs of the `pre` block
+  float* x_save;                // optional [N][256]: copy of the `pre` block's input h_node (backward pass)
+  float* agg_save;              // optional [N][256]: copy of the `mid` block's aggregated messages
   const float* pos_cur;
   float* pos_nxt;
   float* pred_node;             // kind 1 decode target [N][kn]
@@ -149,6 +152,67 @@ __device__ __forceinline__ void store_table(const float (&acc)[8][N / 32], float
   for (int i = 0; i < 8; ++i) {
     const int n = row0 + warp * 8 + i;
     if (n < n_rows) store_cols<N>(acc[i], table + (size_t)n * N, lane);
+  }
+}
+
+// Per-node hoisted projections of one block from the h_node tile X (smem): everything a first-layer Linear
+// of the reference applies to a gathered node feature is applied per node here and gathered afterwards.
+__device__ __forceinline__ void node_pre_phase(const float* __restrict__ blob, const BlkOff& off, const Tables& tb,
+                                               const float* X, float* A, float* Ws, const float* tns, int row0,
+                                               int n_nodes, float* fl_dst, float* fr_dst, float* sl_clear) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {  // node_net(x)                                                                graph.py:39
+    float acc[8][8];
+    tile_gemm<D, D>(acc, X, D, W_(NB_NN1_W), Ws);
+    add_rowvec<D>(acc, W_(NB_NN1_B), lane);
+    layernorm_rows<D, true>(acc, W_(NB_NN1_G), W_(NB_NN1_BE), lane);
+    store_smem<D>(acc, A, D, warp, lane);
+    tile_gemm<D, D>(acc, A, D, W_(NB_NN2_W), Ws);
+    add_rowvec<D>(acc, W_(NB_NN2_B), lane);
+    store_table<D>(acc, tb.hn, row0, n_nodes, warp, lane);
+  }
+  {  // node + time + bias part of gate.net.0 (hoisted from the per-edge cat)      graph.py:46
+    float acc[8][8];
+    tile_gemm<D, D>(acc, X, D, W_(NB_GX_W), Ws);
+    add_rowvec<D>(acc, W_(NB_G1_B), lane);
+    add_scaled_rowvec<D>(acc, W_(NB_GT_W), tns + warp * 8, lane);
+    store_table<D>(acc, tb.gx, row0, n_nodes, warp, lane);
+  }
+  {  // centroid_lin(x)                                                            graph.py:51
+    float acc[8][8];
+    tile_gemm<D, D>(acc, X, D, W_(NB_CEN_W), Ws);
+    add_rowvec<D>(acc, W_(NB_CEN_B), lane);
+    store_table<D>(acc, tb.cen, row0, n_nodes, warp, lane);
+  }
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {   // EdgeBlock hoists                     graph.py:135,139,288-289
+    {
+      float acc[8][4];
+      tile_gemm<D, 128>(acc, X, D, side ? W_(ER_NL_W) : W_(EL_NL_W), Ws);
+      store_table<128>(acc, side ? tb.nlr : tb.nll, row0, n_nodes, warp, lane);
+    }
+    {
+      float acc[8][1];
+      tile_gemm<D, 32>(acc, X, D, side ? W_(ER_GN_W) : W_(EL_GN_W), Ws);
+      add_rowvec<32>(acc, side ? W_(ER_G1_B) : W_(EL_G1_B), lane);   // the time column uses the EDGE time: added per edge
+      store_table<32>(acc, side ? tb.gnr : tb.gnl, row0, n_nodes, warp, lane);
+    }
+    {
+      float acc[8][2];
+      tile_gemm<D, C>(acc, X, D, side ? W_(EB_NFR_W) : W_(EB_NFL_W), Ws);
+      add_rowvec<C>(acc, side ? W_(EB_NFR_B) : W_(EB_NFL_B), lane);
+      // separately buffered per block: edge_kernel_d(i) still reads block i's values after block i+1's were written
+      store_table<C>(acc, side ? fr_dst : fl_dst, row0, n_nodes, warp, lane);
+    }
+  }
+  if (sl_clear) {  // clear the SL/SR accumulators the block's edge_kernel_b will add into
+    for (int i = tid; i < TM * C; i += NTHREADS) {
+      const int n = row0 + i / C;
+      if (n < n_nodes) {
+        sl_clear[(size_t)row0 * C + i] = 0.f;
+        sl_clear[(size_t)n_nodes * C + (size_t)row0 * C + i] = 0.f;
+      }
+    }
   }
 }
 
@@ -185,6 +249,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_kernel(const NodeArgs a) {
           float u[8], v[8];
           load_cols<D>(u, tb.cen + (size_t)n * D, lane);
           load_cols<D>(v, tb.agg + (size_t)n * D, lane);
+#pragma unroll
+          if (a.agg_save) store_cols<D>(v, a.agg_save + (size_t)n * D, lane);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { acc[i][j] = u[j] + v[j]; v[j] = 0.f; }
           store_cols<D>(v, tb.agg + (size_t)n * D, lane);   // re-arm the accumulator for the next block
@@ -225,60 +291,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_kernel(const NodeArgs a) {
   }
 
   if (a.do_pre) {
-    const BlkOff& off = a.pre;
-    {  // node_net(x)                                                                graph.py:39
-      float acc[8][8];
-      tile_gemm<D, D>(acc, X, D, W_(NB_NN1_W), Ws);
-      add_rowvec<D>(acc, W_(NB_NN1_B), lane);
-      layernorm_rows<D, true>(acc, W_(NB_NN1_G), W_(NB_NN1_BE), lane);
-      store_smem<D>(acc, A, D, warp, lane);
-      tile_gemm<D, D>(acc, A, D, W_(NB_NN2_W), Ws);
-      add_rowvec<D>(acc, W_(NB_NN2_B), lane);
-      store_table<D>(acc, tb.hn, row0, a.n_nodes, warp, lane);
-    }
-    {  // node + time + bias part of gate.net.0 (hoisted from the per-edge cat)      graph.py:46
-      float acc[8][8];
-      tile_gemm<D, D>(acc, X, D, W_(NB_GX_W), Ws);
-      add_rowvec<D>(acc, W_(NB_G1_B), lane);
-      add_scaled_rowvec<D>(acc, W_(NB_GT_W), tns + warp * 8, lane);
-      store_table<D>(acc, tb.gx, row0, a.n_nodes, warp, lane);
-    }
-    {  // centroid_lin(x)                                                            graph.py:51
-      float acc[8][8];
-      tile_gemm<D, D>(acc, X, D, W_(NB_CEN_W), Ws);
-      add_rowvec<D>(acc, W_(NB_CEN_B), lane);
-      store_table<D>(acc, tb.cen, row0, a.n_nodes, warp, lane);
-    }
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {   // EdgeBlock hoists                     graph.py:135,139,288-289
-      {
-        float acc[8][4];
-        tile_gemm<D, 128>(acc, X, D, side ? W_(ER_NL_W) : W_(EL_NL_W), Ws);
-        store_table<128>(acc, side ? tb.nlr : tb.nll, row0, a.n_nodes, warp, lane);
-      }
-      {
-        float acc[8][1];
-        tile_gemm<D, 32>(acc, X, D, side ? W_(ER_GN_W) : W_(EL_GN_W), Ws);
-        add_rowvec<32>(acc, side ? W_(ER_G1_B) : W_(EL_G1_B), lane);   // the time column uses the EDGE time: added per edge
-        store_table<32>(acc, side ? tb.gnr : tb.gnl, row0, a.n_nodes, warp, lane);
-      }
-      {
-        float acc[8][2];
-        tile_gemm<D, C>(acc, X, D, side ? W_(EB_NFR_W) : W_(EB_NFL_W), Ws);
-        add_rowvec<C>(acc, side ? W_(EB_NFR_B) : W_(EB_NFL_B), lane);
-        // parity-buffered: edge_kernel_d(i) still reads block i's values after this kernel wrote block i+1's
-        store_table<C>(acc, (side ? tb.fr : tb.fl) + (size_t)a.par_next * a.n_nodes * C, row0, a.n_nodes, warp, lane);
+    if (a.x_save) {
+      for (int i = tid; i < TM * D / 4; i += NTHREADS) {
+        const int r = i / (D / 4), c4 = i % (D / 4);
+        const int n = row0 + r;
+        if (n < a.n_nodes) reinterpret_cast<float4*>(a.x_save + (size_t)n * D)[c4] = reinterpret_cast<const float4*>(X + r * D)[c4];
       }
     }
-    // clear the SL/SR accumulators the next edge_kernel_b will add into
-    float* sl = tb.slsr + (size_t)a.par_next * 2 * a.n_nodes * C;
-    for (int i = tid; i < TM * C; i += NTHREADS) {
-      const int n = row0 + i / C;
-      if (n < a.n_nodes) {
-        sl[(size_t)row0 * C + i] = 0.f;
-        sl[(size_t)a.n_nodes * C + (size_t)row0 * C + i] = 0.f;
-      }
-    }
+    node_pre_phase(blob, a.pre, tb, X, A, Ws, tns, row0, a.n_nodes, a.fl_next, a.fr_next, a.sl_next);
   }
 
   if (a.do_dec) {
@@ -316,7 +336,9 @@ struct EdgeArgs {
   const int *left, *right;
   int n_nodes, n_edges;
   int update_pos;
-  int par;                    // SL/SR parity of this block
+  float* sl;                  // [2 (SL,SR)][N][64] scatter targets of this block's BondFFNs
+  const float *fl, *fr;       // [N][64] node_ffn_{left,right}(h_node) of this block
+  float* ebuf;                // [E][64] e = edge_embs(cat(h_edge, rbf)) of this block
   float rbf_lo, rbf_hi;
   const float* pos_cur;
   float* pos_nxt;
@@ -388,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_b(const EdgeArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int q = q0 + warp * 8 + i;
-      if (q < a.n_edges) store_cols<C>(acc[i], tb.ebuf + (size_t)q * C, lane);
+      if (q < a.n_edges) store_cols<C>(acc[i], a.ebuf + (size_t)q * C, lane);
     }
   }
   // ---- NodeBlock edge path                                                       graph.py:42-50
@@ -416,7 +438,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_b(const EdgeArgs a) {
     scatter_add_rows<D, true>(acc, tb.agg, lw, lane);        // scatter_sum over row (= left)
   }
   // ---- EdgeBlock: bond_ffn_left (node = left, scattered to right) and _right      graph.py:278-284
-  float* sl = tb.slsr + (size_t)a.par * 2 * a.n_nodes * C;
+  float* sl = a.sl;
   float* sr = sl + (size_t)a.n_nodes * C;
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
@@ -478,13 +500,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_d(const EdgeArgs a) {
     const int r = i / (C / 4), c4 = i % (C / 4);
     const int q = q0 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < a.n_edges) v = reinterpret_cast<const float4*>(tb.ebuf + (size_t)q * C)[c4];
+    if (q < a.n_edges) v = reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C)[c4];
     reinterpret_cast<float4*>(Es + r * C)[c4] = v;
   }
   __syncthreads();
   const int* lw = ls + warp * 8;
   const int* rw = rs + warp * 8;
-  const float* sl = tb.slsr + (size_t)a.par * 2 * a.n_nodes * C;
+  const float* sl = a.sl;
   const float* sr = sl + (size_t)a.n_nodes * C;
   {  // graph.py:286-294
     float acc[8][2];
@@ -492,8 +514,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_d(const EdgeArgs a) {
     add_rowvec<C>(acc, W_(EB_SELF_B), lane);
     gather_rows<C, false>(acc, sl, lw, lane);       // scatter_sum(msg_left, right)[left]
     gather_rows<C, false>(acc, sr, rw, lane);       // scatter_sum(msg_right, left)[right]
-    gather_rows<C, false>(acc, tb.fl + (size_t)a.par * a.n_nodes * C, lw, lane);   // node_ffn_left(h_node[left])
-    gather_rows<C, false>(acc, tb.fr + (size_t)a.par * a.n_nodes * C, rw, lane);   // node_ffn_right(h_node[right])
+    gather_rows<C, false>(acc, a.fl, lw, lane);     // node_ffn_left(h_node[left])
+    gather_rows<C, false>(acc, a.fr, rw, lane);     // node_ffn_right(h_node[right])
     layernorm_rows<C, true>(acc, W_(EB_LN_G), W_(EB_LN_BE), lane);
     store_smem<C>(acc, A, C, warp, lane);
     tile_gemm<C, C>(acc, A, C, W_(EB_OUT_W), Ws);
@@ -689,6 +711,35 @@ size_t carve(Tables& tb, float* base, int64_t N, int64_t E) {
   return o;
 }
 
+// Extra workspace of a forward that will be followed by the input-gradient backward (bond predictor
+// guidance): per-block inputs that are cheap to keep (per-node tensors and e = edge_embs output); every
+// other per-edge activation is recomputed tile by tile in the backward kernels.
+struct Saved {
+  float *e;                  // [L][E][64]   e_i
+  float *x;                  // [L][N][256]  h_node entering block i
+  float *agg;                // [L][N][256]  aggregated NodeBlock messages of block i
+  float *slsr;               // [L][2][N][64]
+  float *dx;                 // [N][256]  running d/d h_node
+  float *dh, *de;            // [E][64]   d/d h_edge (block output -> block input), d/d e
+  float *dg;                 // [E][16]   d/d rbf features, summed over blocks
+  float *dul, *dur;          // [N][64]   sum_{p: l_p = n} du_p, sum_{p: r_p = n} du_p
+  float *dagg, *dgx, *dhn;   // [N][256]
+  float *dnl;                // [2][N][128]
+  float *dgn;                // [2][N][32]
+  float *ddect;              // [N][64]
+};
+
+size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
+  size_t o = 0;
+  auto take = [&](size_t n) { float* p = base ? base + o : nullptr; o += al(n); return p; };
+  sv.e = take(L * E * C); sv.x = take(L * N * D); sv.agg = take(L * N * D); sv.slsr = take(L * 2 * N * C);
+  sv.dx = take(N * D); sv.dh = take(E * C); sv.de = take(E * C); sv.dg = take(E * G);
+  sv.dul = take(N * C); sv.dur = take(N * C);
+  sv.dagg = take(N * D); sv.dgx = take(N * D); sv.dhn = take(N * D);
+  sv.dnl = take(2 * N * 128); sv.dgn = take(2 * N * 32); sv.ddect = take(N * C);
+  return o;
+}
+
 constexpr size_t SMEM_NODE = (2 * TM * D + 2 * WCHUNK + TM) * sizeof(float);
 constexpr size_t SMEM_EDGE_B = (TM * C + 2 * TM * D + 2 * WCHUNK + TM + 4 * TM + 2 * TM) * sizeof(float);
 constexpr size_t SMEM_EDGE_D = (3 * TM * C + TM * D + 2 * WCHUNK + TM + 4 * TM + 2 * TM) * sizeof(float);
@@ -731,12 +782,19 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   if (net->kind != 0 && (plan->n_half * 2 != E)) return fail(MDB_EINVAL, "edges must be (half, flipped half)%s");
   if (net->num_node_types > 32 || net->num_edge_types > 32) return fail(MDB_EINVAL, "too many types%s");
   if (net->time_dim < 0 || net->time_dim >= C) return fail(MDB_EINVAL, "time_dim out of range%s");
-  if (mdb_workspace_bytes(N, E, 0, L) > workspace_bytes) return fail(MDB_EINVAL, "workspace too small%s");
+  if (mdb_workspace_bytes(N, E, in.save ? 1 : 0, L) > workspace_bytes) return fail(MDB_EINVAL, "workspace too small%s");
   int rc = ensure_attrs();
   if (rc) return rc;
 
   Tables tb;
-  carve(tb, workspace, N, E);
+  const size_t tb_floats = carve(tb, workspace, N, E);
+  Saved sv;
+  memset(&sv, 0, sizeof(sv));
+  if (in.save) carve_saved(sv, workspace + tb_floats, N, E, L);
+  const size_t NC = (size_t)N * C, ND = (size_t)N * D, EC = (size_t)E * C;
+  auto sl_of = [&](int i) { return in.save ? sv.slsr + (size_t)i * 2 * NC : tb.slsr + (size_t)(i & 1) * 2 * NC; };
+  auto fl_of = [&](int i) { return tb.fl + (size_t)(i & 1) * NC; };
+  auto fr_of = [&](int i) { return tb.fr + (size_t)(i & 1) * NC; };
   HeadOff head;
   for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
   const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
@@ -762,7 +820,9 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   na.kind = net->kind; na.kn = net->num_node_types; na.pred_node = in.out_node;
   // pre(0)
   fill_blk(na.pre, net, 0);
-  na.do_mid = 0; na.do_pre = 1; na.do_dec = 0; na.par_next = 0; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
+  na.do_mid = 0; na.do_pre = 1; na.do_dec = 0; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
+  na.sl_next = sl_of(0); na.fl_next = fl_of(0); na.fr_next = fr_of(0);
+  na.x_save = in.save ? sv.x : nullptr; na.agg_save = nullptr;
   LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
 
   EdgeArgs ea;
@@ -773,12 +833,16 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 
   for (int i = 0; i < L; ++i) {
     fill_blk(ea.off, net, i);
-    ea.par = i & 1; ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
+    ea.sl = sl_of(i); ea.fl = fl_of(i); ea.fr = fr_of(i); ea.ebuf = in.save ? sv.e + (size_t)i * EC : tb.ebuf;
+    ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
     if (E > 0) LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
     fill_blk(na.mid, net, i);
     na.do_mid = 1; na.do_pre = (i + 1 < L); na.do_dec = (i + 1 == L) && net->kind != 0;
     if (na.do_pre) fill_blk(na.pre, net, i + 1);
-    na.par_next = (i + 1) & 1; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
+    na.sl_next = sl_of(i + 1 < L ? i + 1 : i); na.fl_next = fl_of(i + 1); na.fr_next = fr_of(i + 1);
+    na.x_save = (in.save && i + 1 < L) ? sv.x + (size_t)(i + 1) * ND : nullptr;
+    na.agg_save = in.save ? sv.agg + (size_t)i * ND : nullptr;
+    na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
     LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
     if (E > 0) LAUNCH(MDB_K_edge_d, st, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea)));
     if (net->update_pos) { const float* t_ = pos_cur; pos_cur = pos_nxt; pos_nxt = const_cast<float*>(t_); }
@@ -801,14 +865,20 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   return MDB_OK;
 }
 
+#include "mdb_backward.cuh"
+
 }  // namespace
 
 extern "C" {
 
 size_t mdb_workspace_bytes(int64_t n_nodes, int64_t n_edges, int32_t with_backward, int32_t num_blocks) {
-  (void)with_backward; (void)num_blocks;
   Tables tb;
-  return carve(tb, nullptr, n_nodes, n_edges) * sizeof(float);
+  size_t n = carve(tb, nullptr, n_nodes, n_edges);
+  if (with_backward) {
+    Saved sv;
+    n += carve_saved(sv, nullptr, n_nodes, n_edges, num_blocks);
+  }
+  return n * sizeof(float);
 }
 
 int mdb_net_forward(const mdb_net_desc* net, const mdb_plan* plan, const float* h_node_in, const float* pos_in,
@@ -848,9 +918,11 @@ int mdb_bondpred_forward(const mdb_net_desc* net, const mdb_plan* plan, const fl
   return run_forward(net, plan, in, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int mdb_bondpred_backward(const mdb_net_desc*, const mdb_plan*, const float*, const float*, const int64_t*,
-                          const int64_t*, const int64_t*, const float*, float*, float*, size_t, void*) {
-  return fail(MDB_EINVAL, "mdb_bondpred_backward: backward kernels not built yet%s");
+int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const float* h_node, const float* pos,
+                          const int64_t* batch_node, const int64_t* batch_edge, const int64_t* t,
+                          const float* d_logits, float* d_pos, float* workspace, size_t workspace_bytes, void* stream) {
+  (void)h_node; (void)batch_node; (void)batch_edge; (void)t;   // everything they determine was saved by the forward
+  return run_bondpred_backward(net, plan, pos, d_logits, d_pos, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 void mdb_profile_begin(void) {

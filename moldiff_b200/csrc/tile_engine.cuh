@@ -209,6 +209,66 @@ __device__ __forceinline__ void layernorm_rows(float (&acc)[8][N / 32], const fl
   }
 }
 
+// LayerNorm forward that keeps what the backward needs: acc <- xhat = (x - mean) * rstd, rstd[i] per row.
+template <int N>
+__device__ __forceinline__ void ln_xhat(float (&acc)[8][N / 32], float (&rstd)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) s += acc[i][j];
+    const float mean = warp_sum(s) * (1.f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) { const float d = acc[i][j] - mean; q = fmaf(d, d, q); }
+    rstd[i] = 1.f / sqrtf(warp_sum(q) * (1.f / N) + LN_EPS);
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) acc[i][j] = (acc[i][j] - mean) * rstd[i];
+  }
+}
+
+// acc (= xhat) <- relu(xhat * gamma + beta)
+template <int N>
+__device__ __forceinline__ void affine_relu(float (&acc)[8][N / 32], const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, int lane) {
+  float g[N / 32], b[N / 32];
+  load_cols<N>(g, gamma, lane);
+  load_cols<N>(b, beta, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < N / 32; ++j) acc[i][j] = fmaxf(acc[i][j] * g[j] + b[j], 0.f);
+}
+
+// One row of the backward of y = relu(LN(x) * gamma + beta):  d (grad wrt y) <- grad wrt x.
+//   dxhat = d * 1[xhat*g + b > 0] * g ;  dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))
+template <int N>
+__device__ __forceinline__ void ln_relu_bwd_row(float (&d)[N / 32], const float (&xh)[N / 32], float rstd,
+                                                const float (&g)[N / 32], const float (&b)[N / 32]) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < N / 32; ++j) {
+    const float y = xh[j] * g[j] + b[j];
+    d[j] = (y > 0.f) ? d[j] * g[j] : 0.f;
+    s1 += d[j];
+    s2 = fmaf(d[j], xh[j], s2);
+  }
+  const float m1 = warp_sum(s1) * (1.f / N), m2 = warp_sum(s2) * (1.f / N);
+#pragma unroll
+  for (int j = 0; j < N / 32; ++j) d[j] = rstd * (d[j] - m1 - xh[j] * m2);
+}
+
+// All 8 rows, d and xhat both in registers.
+template <int N>
+__device__ __forceinline__ void ln_relu_bwd(float (&d)[8][N / 32], const float (&xh)[8][N / 32], const float (&rstd)[8],
+                                            const float* __restrict__ gamma, const float* __restrict__ beta, int lane) {
+  float g[N / 32], b[N / 32];
+  load_cols<N>(g, gamma, lane);
+  load_cols<N>(b, beta, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ln_relu_bwd_row<N>(d[i], xh[i], rstd[i], g, b);
+}
+
 template <int N>
 __device__ __forceinline__ void sigmoid_rows(float (&acc)[8][N / 32]) {
 #pragma unroll

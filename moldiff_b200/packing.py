@@ -80,6 +80,53 @@ def _bond_ffn(sd, p, tag, out, bond_dim, node_dim):
     out[f"{tag}_G2_B"] = sd[f"{p}.gate.net.3.bias"]
 
 
+def _asis(w):
+    """Linear.weight [out][in] kept as stored: the [K][N] operand of dX = dY @ W."""
+    return w.detach().to(torch.float32).contiguous()
+
+
+def _pad_rows(m, n):
+    out = torch.zeros(n, m.shape[1], dtype=torch.float32)
+    out[: m.shape[0]] = m
+    return out
+
+
+def block_backward_tensors(sd, net_prefix, i):
+    """Transposed-use copies for the input-gradient backward kernels (bond predictor guidance)."""
+    o = {}
+    ee = sd[f"{net_prefix}.edge_embs.{i}.weight"]                  # [64][80]
+    o["T_EEH"] = _asis(ee[:, :EDGE_DIM])
+    o["T_EEG"] = _pad_cols(_asis(ee[:, EDGE_DIM:]), 32)
+    nb = f"{net_prefix}.node_blocks_with_edge.{i}"
+    o["T_NB_NN1"] = _asis(sd[nb + ".node_net.net.0.weight"])
+    o["T_NB_NN2"] = _asis(sd[nb + ".node_net.net.3.weight"])
+    o["T_NB_EN1"] = _asis(sd[nb + ".edge_net.net.0.weight"])
+    o["T_NB_EN2"] = _asis(sd[nb + ".edge_net.net.3.weight"])
+    o["T_NB_MSG"] = _asis(sd[nb + ".msg_net.weight"])
+    g0 = sd[nb + ".gate.net.0.weight"]
+    o["T_NB_GE"] = _asis(g0[:, :EDGE_DIM])
+    o["T_NB_GX"] = _asis(g0[:, EDGE_DIM:EDGE_DIM + NODE_DIM])
+    o["T_NB_G2"] = _asis(sd[nb + ".gate.net.3.weight"])
+    o["T_NB_CEN"] = _asis(sd[nb + ".centroid_lin.weight"])
+    o["T_NB_OUT"] = _asis(sd[nb + ".out_transform.weight"])
+    eb = f"{net_prefix}.edge_blocks.{i}"
+    for tag, sub in (("EL", "bond_ffn_left"), ("ER", "bond_ffn_right")):
+        p = f"{eb}.{sub}"
+        o[f"T_{tag}_BL"] = _asis(sd[p + ".bond_linear.weight"])
+        o[f"T_{tag}_NL"] = _asis(sd[p + ".node_linear.weight"])
+        o[f"T_{tag}_I1"] = _asis(sd[p + ".inter_module.net.0.weight"])
+        o[f"T_{tag}_I2"] = _asis(sd[p + ".inter_module.net.3.weight"])
+        g0 = sd[p + ".gate.net.0.weight"]
+        o[f"T_{tag}_GB"] = _asis(g0[:, :EDGE_DIM])
+        o[f"T_{tag}_GN"] = _asis(g0[:, EDGE_DIM:EDGE_DIM + NODE_DIM])
+        o[f"T_{tag}_G2"] = _asis(sd[p + ".gate.net.3.weight"])
+    o["T_EB_NFL"] = _asis(sd[eb + ".node_ffn_left.weight"])
+    o["T_EB_NFR"] = _asis(sd[eb + ".node_ffn_right.weight"])
+    o["T_EB_SELF"] = _asis(sd[eb + ".self_ffn.weight"])
+    o["T_EB_OUT"] = _asis(sd[eb + ".out_transform.weight"])
+    return o
+
+
 def block_tensors(sd, net_prefix, i, update_pos):
     """All slot tensors of block i, keyed by slot name."""
     o = {}
@@ -160,6 +207,10 @@ def head_tensors(sd, kind, net_prefix, time_dim):
         o["EDEC3_BE"] = sd["edge_decoder.net.4.bias"]
         o["EDEC3_W"] = _pad_cols(_t(sd["edge_decoder.net.6.weight"]), 32)
         o["EDEC3_B"] = _pad_vec(sd["edge_decoder.net.6.bias"], 32)
+        o["T_EDEC1"] = _asis(w0[:, :EDGE_DIM])
+        o["T_EDEC1N"] = _asis(w0[:, EDGE_DIM:])
+        o["T_EDEC2"] = _asis(sd["edge_decoder.net.3.weight"])
+        o["T_EDEC3"] = _pad_rows(_asis(sd["edge_decoder.net.6.weight"]), 32)
     return o
 
 
@@ -185,6 +236,8 @@ def pack_network(sd, *, kind, net_prefix, num_blocks, update_pos, time_dim=0):
     block_off = []
     for i in range(num_blocks):
         bt = block_tensors(sd, net_prefix, i, update_pos)
+        if kind == 2:
+            bt.update(block_backward_tensors(sd, net_prefix, i))
         unknown = set(bt) - set(BLOCK_SLOTS)
         if unknown:
             raise RuntimeError(f"packer produced unknown slots {sorted(unknown)}")

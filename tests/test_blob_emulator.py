@@ -61,3 +61,36 @@ def test_bare_net_shuffled_edges(seeded_models):
                          node_time=nt, edge_time=et)
     for a, b in zip(out, ref):
         assert R.rel_err(a, b) < TOL
+
+
+def test_bondpred_backward_dataflow(seeded_models):
+    """Manual input-gradient chain (what mdb_backward.cuh implements) == autograd through the oracle: exact in
+    fp64 (1e-12), and in fp32 as reproducible as the reference's own gradient (see assert_gradient_parity)."""
+    from tests.helpers import assert_gradient_parity
+    sd = seeded_models[1].state_dict()
+    inp = batch_inputs(B=8, t_values=(999, 400, 0, 650))
+    ei, be, _ = doubled(inp)
+    g = torch.Generator().manual_seed(3)
+    d_logits = torch.randn(ei.shape[1] // 2, 5, generator=g)
+    res = {}
+    for dtype in (torch.float64, torch.float32):
+        sdd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+        pos = inp["pos"].to(dtype).clone().requires_grad_(True)
+        logits_ref = R.bondpred_forward(sdd, inp["h_node"].to(dtype), pos, inp["batch_node"], ei, be, inp["t"])
+        grad_ref = torch.autograd.grad((logits_ref * d_logits.to(dtype)).sum(), pos)[0]
+        blob, ho, bo = packing.pack_network(sd, kind=2, net_prefix="encoder", num_blocks=8, update_pos=False, time_dim=20)
+        torch.set_default_dtype(dtype)
+        try:
+            with torch.no_grad():
+                logits, d_pos = BE.bondpred_forward_backward(
+                    BE.Blob(blob.to(dtype), ho, bo), num_blocks=8, rbf_lo=0.0, rbf_hi=20.0, time_dim=20, T=1000.0,
+                    kn=8, ke=5, h_node_in=inp["h_node"].to(dtype), pos=inp["pos"].to(dtype), edge_index=ei,
+                    batch_node=inp["batch_node"], batch_edge=be, t=inp["t"], d_logits=d_logits.to(dtype))
+        finally:
+            torch.set_default_dtype(torch.float32)
+        res[dtype] = (logits, d_pos, logits_ref.detach(), grad_ref)
+    l64, d64, lr64, g64 = res[torch.float64]
+    assert R.rel_err(l64, lr64) < 1e-12 and R.rel_err(d64, g64) < 1e-10      # the formulas are exact
+    l32, d32, lr32, g32 = res[torch.float32]
+    assert R.rel_err(l32, lr32) < TOL
+    assert_gradient_parity(d32, g32, g64, inp["batch_node"], "emulator fp32")
