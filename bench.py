@@ -267,7 +267,8 @@ def main():
     if rank == 0:
         prof = engine.profile_kernels(lambda: step(0), reps=3)
         pk = peaks()
-        name, info = max(prof.items(), key=lambda kv: kv[1]["ms_total"])
+        name, info = max(((k, v) for k, v in prof.items() if k in engine.KERNEL_LOGICAL_FLOP_PER_EDGE),
+                         key=lambda kv: kv[1]["ms_total"])
         avg_ms = info["ms_total"] / max(info["launches"], 1)
         flop = engine.KERNEL_LOGICAL_FLOP_PER_EDGE.get(name, 0.0) * E
         achieved = flop / (avg_ms * 1e-3) / 1e12

@@ -109,6 +109,9 @@ KERNEL_LOGICAL_FLOP_PER_EDGE = {
     # EdgeBlock tail (node_ffn L/R 256->64, self 64->64, out 64->64) + PosUpdate as written
     "edge_d": 2.0 * (2 * 256 * 64 + 64 * 64 + 64 * 64
                      + 2 * (256 * 64 + 64 * 64) + 64 * 256 + 64 * 256 + 256 * 256 + 256 + 129 * 32 + 32),
+    # input-gradient backward of the NodeBlock per-edge Linears as autograd executes them (one dX = dY W per Linear)
+    "bwd_edge_nodeblock": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
+    "bwd_edge_bondffn": 2.0 * (80 * 64 + 2 * (64 * 128 + 256 * 128 + 128 * 128 + 128 * 64 + 321 * 32 + 32 * 64)),
 }
 
 
