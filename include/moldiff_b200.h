@@ -191,6 +191,10 @@ int mdb_profile_end(double* ms_per_class, int64_t* launches_per_class);
 const char* mdb_kernel_class_name(int cls);
 int mdb_num_kernel_classes(void);
 
+/* Self-test of the tcgen05 GEMM pipeline (one 128-row tile): y[128][n] = x[128][k] * W, W given as the packed
+ * split-bf16 stage images of moldiff_b200/packing.py:tc_image; twice != 0 accumulates the product twice. */
+int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int32_t n, int32_t twice, void* stream);
+
 /* Diagnostics. */
 const char* mdb_last_error(void);
 int mdb_version(void);

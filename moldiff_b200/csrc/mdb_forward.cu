@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_kernel(const NodeArgs a) {
           float u[8], v[8];
           load_cols<D>(u, tb.cen + (size_t)n * D, lane);
           load_cols<D>(v, tb.agg + (size_t)n * D, lane);
-#pragma unroll
           if (a.agg_save) store_cols<D>(v, a.agg_save + (size_t)n * D, lane);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { acc[i][j] = u[j] + v[j]; v[j] = 0.f; }
@@ -866,6 +865,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 }
 
 #include "mdb_backward.cuh"
+#include "tc_selftest.cuh"
 
 }  // namespace
 
@@ -923,6 +923,16 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
                           const float* d_logits, float* d_pos, float* workspace, size_t workspace_bytes, void* stream) {
   (void)h_node; (void)batch_node; (void)batch_edge; (void)t;   // everything they determine was saved by the forward
   return run_bondpred_backward(net, plan, pos, d_logits, d_pos, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int32_t n, int32_t twice, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 64 && n == 256) return launch_tc_selftest<64, 256>(x, w_img, y, twice, st);
+  if (k == 256 && n == 256) return launch_tc_selftest<256, 256>(x, w_img, y, twice, st);
+  if (k == 256 && n == 64) return launch_tc_selftest<256, 64>(x, w_img, y, twice, st);
+  if (k == 128 && n == 128) return launch_tc_selftest<128, 128>(x, w_img, y, twice, st);
+  if (k == 64 && n == 32) return launch_tc_selftest<64, 32>(x, w_img, y, twice, st);
+  return fail(MDB_EINVAL, "mdb_tc_selftest: unsupported (k, n)%s");
 }
 
 void mdb_profile_begin(void) {

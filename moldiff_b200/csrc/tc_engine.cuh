@@ -1,0 +1,173 @@
+// tcgen05 / TMEM / bulk-copy primitives for the sm_100a tensor-core path (inline PTX, no CUTLASS).
+//
+// GEMM convention used by every caller:   D[128 rows][N] (+)= A[128][K] * W[K][N]
+//   * A: activation tile produced by the epilogue threads (one thread per row), stored in shared memory as two
+//     bf16 planes (hi, lo) in the UMMA K-major SWIZZLE_NONE canonical layout: 8-row x 16-byte core matrices,
+//     byte offset of element (r, k):  (r % 8) * 16 + (r / 8) * SBO + (k / 8) * LBO + (k % 8) * 2
+//     with LBO = 128 (K-adjacent core matrices contiguous) and SBO = (K / 8) * 128.
+//   * W: pre-packed on the host (moldiff_b200/packing.py: tc_images) as per-K-stage images of the
+//     "N x K, K-major" B operand in the same canonical layout, hi plane then lo plane, so that one
+//     cp.async.bulk per plane brings a stage in.
+//   * fp32 parity: split-bf16, three MMAs per K step accumulate hi*hi + lo*hi + hi*lo into the same TMEM tile
+//     (1.7e-5 end-to-end vs the 1e-4 bar; single-pass bf16 is 1e-2).
+//   * D: TMEM, lane = row, column = n (fp32).  Read back with tcgen05.ld 32x32b (thread t of warp w owns lane
+//     32 * (w % 4) + t).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// Bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- bulk async copy global -> shared (TMA engine, 1-D; SASS UBLKCP) ---------------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM ---------------------------------------------------------------------------------------------
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {     // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- descriptors ----------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_NONE (layout_type 0), sm_100 version field = 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]   -- issued by ONE thread
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed (implies before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- TMEM -> registers: 32 consecutive fp32 columns of this thread's lane ------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- split-bf16 helpers -----------------------------------------------------------------------------------
+// 8 consecutive k values of one row -> one 16-byte chunk in the hi plane and one in the lo plane.
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// byte offset of the 16-byte chunk (row r, k-chunk c) in an A plane with K columns (LBO = 128, SBO = K/8*128)
+template <int K>
+__device__ __forceinline__ uint32_t a_chunk_off(int r, int c) {
+  return (uint32_t)((r & 7) * 16 + (r >> 3) * (K / 8) * 128 + c * 128);
+}
+
+// Store 32 consecutive fp32 values of row r, starting at column k0 (multiple of 8), into the A planes.
+template <int K>
+__device__ __forceinline__ void store_a32(uint8_t* a_hi, uint8_t* a_lo, int r, int k0, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = v[c * 8 + i];
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const uint32_t off = a_chunk_off<K>(r, k0 / 8 + c);
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  }
+}
+
+// One weight matrix streamed in K stages of KB columns: stage image = [hi plane | lo plane], each N*KB*2 bytes.
+template <int N, int KB>
+struct WStage {
+  static constexpr uint32_t PLANE_BYTES = (uint32_t)N * KB * 2;
+  static constexpr uint32_t STAGE_BYTES = 2 * PLANE_BYTES;
+  static constexpr uint32_t SBO = (KB / 8) * 128;
+};
+
+}  // namespace tc

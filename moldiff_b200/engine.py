@@ -82,6 +82,8 @@ def load_library():
         lib.mdb_bondpred_forward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 6 + [i32, vp, sz, vp]
         lib.mdb_bondpred_backward.restype = C.c_int
         lib.mdb_bondpred_backward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 8 + [sz, vp]
+        lib.mdb_tc_selftest.restype = C.c_int
+        lib.mdb_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
         lib.mdb_profile_begin.restype = None
         lib.mdb_profile_end.restype = C.c_int
         lib.mdb_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -317,3 +319,15 @@ def bondpred_backward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, 
                                    ws.data_ptr(), ws.numel() * 4, _stream_ptr(pos.device))
     _check(rc, "mdb_bondpred_backward")
     return d_pos
+
+
+def tc_selftest(x, w_kn, twice=False):
+    """y = x @ w (x [128][K], w [K][N]) through the tcgen05 split-bf16 pipeline (tests only)."""
+    lib = load_library()
+    x = _dev_f32(x, "x")
+    k, n = w_kn.shape
+    img = packing.tc_image(w_kn.cpu()).to(x.device)
+    y = torch.empty(128, n, dtype=torch.float32, device=x.device)
+    rc = lib.mdb_tc_selftest(x.data_ptr(), img.data_ptr(), y.data_ptr(), k, n, 1 if twice else 0, _stream_ptr(x.device))
+    _check(rc, "mdb_tc_selftest")
+    return y

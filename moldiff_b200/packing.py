@@ -243,3 +243,37 @@ def pack_network(sd, *, kind, net_prefix, num_blocks, update_pos, time_dim=0):
             raise RuntimeError(f"packer produced unknown slots {sorted(unknown)}")
         block_off.append([put(bt[s]) if s in bt else -1 for s in BLOCK_SLOTS])
     return torch.cat(chunks), head_off, block_off
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core operand images (tcgen05 path)
+# ---------------------------------------------------------------------------------------------------------
+TC_KB = 32   # K columns per weight stage; must equal tc::KB in csrc/tc_pipe.cuh
+
+
+def split_bf16(w):
+    """fp32 -> (hi, lo) bf16 pair with hi + lo ~= w to ~2^-17 relative (round-to-nearest-even both times)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi, lo
+
+
+def _canonical_plane(wt_stage):
+    """[N][KB] bf16 (the 'N x K, K-major' B operand of one stage) -> UMMA SWIZZLE_NONE K-major canonical image:
+    byte offset of (n, k) = (n % 8) * 16 + (n / 8) * (KB / 8) * 128 + (k / 8) * 128 + (k % 8) * 2."""
+    n, kb = wt_stage.shape
+    return wt_stage.reshape(n // 8, 8, kb // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
+
+
+def tc_image(w_kn):
+    """W[K][N] fp32 (y = x @ W) -> int16 tensor holding, for every K stage, [hi plane | lo plane]."""
+    k, n = w_kn.shape
+    if k % TC_KB or n % 16:
+        raise ValueError(f"tc_image: K={k} must be a multiple of {TC_KB} and N={n} of 16")
+    hi, lo = split_bf16(w_kn.detach().to(torch.float32).t().contiguous())   # [N][K]
+    parts = []
+    for s in range(k // TC_KB):
+        sl = slice(s * TC_KB, (s + 1) * TC_KB)
+        parts.append(_canonical_plane(hi[:, sl]))
+        parts.append(_canonical_plane(lo[:, sl]))
+    return torch.cat(parts).view(torch.int16)
