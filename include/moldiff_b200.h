@@ -102,6 +102,20 @@ enum mdb_head_slot {
   MDB_NUM_HEAD_SLOTS
 };
 
+/* Tensor-core operand images of one block (byte offsets into the tc blob): per-K-stage split-bf16 (hi | lo)
+ * planes of the "N x K, K-major" B operand in the UMMA SWIZZLE_NONE canonical layout (csrc/tc_engine.cuh). */
+#define MDB_TC_SLOTS(X)                                                                            \
+  X(NB_EN1) X(NB_EN2) X(NB_MSG) X(NB_GE) X(NB_G2)          /* NodeBlock per-edge Linears, forward   */ \
+  X(BT_NB_G2) X(BT_NB_GE) X(BT_NB_MSG) X(BT_NB_EN2) X(BT_NB_EN1) /* same, transposed use (backward) */ \
+  X(PU_PB) X(PU_PN) X(PU_I1)                                /* PosUpdate edge_lin big Linears        */
+
+enum mdb_tc_slot {
+#define MDB_X(name) MDB_T_##name,
+  MDB_TC_SLOTS(MDB_X)
+#undef MDB_X
+  MDB_NUM_TC_SLOTS
+};
+
 /* Static description of one packed network (host struct, passed by pointer). */
 typedef struct mdb_net_desc {
   const float* blob;            /* device: packed fp32 weights                                   */
@@ -115,6 +129,8 @@ typedef struct mdb_net_desc {
   int32_t kind;                 /* 0 = bare NodeEdgeNet, 1 = MolDiff, 2 = BondPredictor           */
   int64_t head_off[MDB_NUM_HEAD_SLOTS];                        /* float offsets into blob, -1 = absent */
   int64_t block_off[MDB_MAX_BLOCKS][MDB_NUM_BLOCK_SLOTS];
+  const void* tc_blob;          /* device: tensor-core operand images, or NULL = fp32 FFMA path only    */
+  int64_t tc_block_off[MDB_MAX_BLOCKS][MDB_NUM_TC_SLOTS];      /* byte offsets into tc_blob, -1 = absent */
 } mdb_net_desc;
 
 /*
@@ -174,7 +190,8 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 /* Kernel classes, for the per-kernel device timing bench.py reports (order is the ABI). */
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
-  X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)
+  X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_posupdate)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,

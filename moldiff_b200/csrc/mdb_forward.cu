@@ -10,6 +10,7 @@
 //                                              hoisted projections for block i+1
 //     edge_kernel_d(i)   EdgeBlock tail -> h_edge, PosUpdate edge path -> pos
 //   edge_decode                                 edge decoder on h_edge[p] + h_edge[p + E/2]
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -338,6 +339,7 @@ struct EdgeArgs {
   float* sl;                  // [2 (SL,SR)][N][64] scatter targets of this block's BondFFNs
   const float *fl, *fr;       // [N][64] node_ffn_{left,right}(h_node) of this block
   float* ebuf;                // [E][64] e = edge_embs(cat(h_edge, rbf)) of this block
+  int skip_nodeblock;         // the NodeBlock edge path runs in tc_nodeblock_fwd_kernel (tensor cores) instead
   float rbf_lo, rbf_hi;
   const float* pos_cur;
   float* pos_nxt;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) edge_kernel_b(const EdgeArgs a) {
     }
   }
   // ---- NodeBlock edge path                                                       graph.py:42-50
-  {
+  if (!a.skip_nodeblock) {
     float acc[8][8];
     tile_gemm<C, D>(acc, Es, C, W_(NB_EN1_W), Ws);           // edge_net.net.0
     add_rowvec<D>(acc, W_(NB_EN1_B), lane);
@@ -659,6 +661,8 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
   if (q < n_edges) out[(size_t)perm[q] * C + c] = hedge[(size_t)q * C + c];
 }
 
+#include "tc_nodeblock.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -756,6 +760,7 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(edge_kernel_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_EDGE_B));
   CUDA_TRY(cudaFuncSetAttribute(edge_kernel_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_EDGE_D));
   CUDA_TRY(cudaFuncSetAttribute(edge_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DEC));
+  CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB));
   done = true;
   return MDB_OK;
 }
@@ -834,7 +839,18 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     fill_blk(ea.off, net, i);
     ea.sl = sl_of(i); ea.fl = fl_of(i); ea.fr = fr_of(i); ea.ebuf = in.save ? sv.e + (size_t)i * EC : tb.ebuf;
     ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
+    const bool tc_nb = net->tc_blob != nullptr && net->tc_block_off[i][MDB_T_NB_EN1] >= 0;
+    ea.skip_nodeblock = tc_nb ? 1 : 0;
     if (E > 0) LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
+    if (E > 0 && tc_nb) {
+      TcNbArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tb;
+      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
+      ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
+      LAUNCH(MDB_K_tc_nodeblock, st,
+             (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, tc::NTHREADS_TC, SMEM_TC_NB, st>>>(ta)));
+    }
     fill_blk(na.mid, net, i);
     na.do_mid = 1; na.do_pre = (i + 1 < L); na.do_dec = (i + 1 == L) && net->kind != 0;
     if (na.do_pre) fill_blk(na.pre, net, i + 1);

@@ -42,7 +42,7 @@ tc_selftest_kernel(const float* __restrict__ X, const uint8_t* __restrict__ w_im
     tc::fence_before_sync();
   }
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc<256>(ps->tmem_base);
+  if (warp == 4) { __syncwarp(); tc::tmem_dealloc<256>(ps->tmem_base); }
 }
 
 template <int K, int N>

@@ -20,6 +20,7 @@ _lib_lock = threading.Lock()
 
 NUM_HEAD = len(packing.HEAD_SLOTS)
 NUM_BLOCK = len(packing.BLOCK_SLOTS)
+NUM_TC = len(packing.TC_SLOTS)
 MAX_BLOCKS = packing.MAX_BLOCKS
 
 
@@ -37,6 +38,8 @@ class NetDesc(C.Structure):
         ("kind", C.c_int32),
         ("head_off", C.c_int64 * NUM_HEAD),
         ("block_off", (C.c_int64 * NUM_BLOCK) * MAX_BLOCKS),
+        ("tc_blob", C.c_void_p),
+        ("tc_block_off", (C.c_int64 * NUM_TC) * MAX_BLOCKS),
     ]
 
 
@@ -187,6 +190,20 @@ class PackedNet:
         for b in range(MAX_BLOCKS):
             for s in range(NUM_BLOCK):
                 d.block_off[b][s] = block_off[b][s] if b < num_blocks else -1
+        # tensor-core operand images (tcgen05 split-bf16 path); MDB_DISABLE_TC=1 keeps the fp32 FFMA kernels
+        self.tc_blob = None
+        d.tc_blob = None
+        for b in range(MAX_BLOCKS):
+            for s in range(NUM_TC):
+                d.tc_block_off[b][s] = -1
+        if os.environ.get("MDB_DISABLE_TC", "0") != "1":
+            tcb, tco = packing.pack_tc(state_dict, net_prefix=net_prefix, num_blocks=num_blocks,
+                                       update_pos=update_pos, with_backward=(kind == 2))
+            self.tc_blob = tcb.to(self.device)
+            d.tc_blob = self.tc_blob.data_ptr()
+            for b in range(num_blocks):
+                for s in range(NUM_TC):
+                    d.tc_block_off[b][s] = tco[b][s]
         self.desc = d
         self.kind = kind
         self.num_blocks = num_blocks

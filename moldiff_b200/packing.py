@@ -29,6 +29,7 @@ def _parse_slots(macro):
 
 
 BLOCK_SLOTS = _parse_slots("MDB_BLOCK_SLOTS")
+TC_SLOTS = _parse_slots("MDB_TC_SLOTS")
 HEAD_SLOTS = _parse_slots("MDB_HEAD_SLOTS")
 
 
@@ -277,3 +278,49 @@ def tc_image(w_kn):
         parts.append(_canonical_plane(hi[:, sl]))
         parts.append(_canonical_plane(lo[:, sl]))
     return torch.cat(parts).view(torch.int16)
+
+
+def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
+    """[K][N] fp32 matrices (y = x @ W) of block i that run on tensor cores, keyed by MDB_TC_SLOTS name."""
+    nb = f"{net_prefix}.node_blocks_with_edge.{i}"
+    g0 = sd[nb + ".gate.net.0.weight"]
+    o = {
+        "NB_EN1": _t(sd[nb + ".edge_net.net.0.weight"]),       # [64][256]
+        "NB_EN2": _t(sd[nb + ".edge_net.net.3.weight"]),       # [256][256]
+        "NB_MSG": _t(sd[nb + ".msg_net.weight"]),
+        "NB_GE": _t(g0[:, :EDGE_DIM]),                         # [64][256]
+        "NB_G2": _t(sd[nb + ".gate.net.3.weight"]),
+    }
+    if with_backward:                                          # dX = dY @ W  with W stored [out][in] = [K][N]
+        o["BT_NB_G2"] = _asis(sd[nb + ".gate.net.3.weight"])
+        o["BT_NB_GE"] = _asis(g0[:, :EDGE_DIM])                # [256][64]
+        o["BT_NB_MSG"] = _asis(sd[nb + ".msg_net.weight"])
+        o["BT_NB_EN2"] = _asis(sd[nb + ".edge_net.net.3.weight"])
+        o["BT_NB_EN1"] = _asis(sd[nb + ".edge_net.net.0.weight"])   # [256][64]
+    if update_pos:
+        pb = f"{net_prefix}.pos_blocks.{i}.edge_lin"
+        o["PU_PB"] = _t(sd[pb + ".bond_linear.weight"])        # [64][256]
+        o["PU_PN"] = _t(sd[pb + ".node_linear.weight"])        # [64][256]
+        o["PU_I1"] = _t(sd[pb + ".inter_module.net.0.weight"]) # [256][256]
+    return o
+
+
+def pack_tc(sd, *, net_prefix, num_blocks, update_pos, with_backward):
+    """Returns (int16 1-D CPU tensor, block_off list[list[int]] in BYTES, -1 = absent); images 128-byte aligned."""
+    chunks, cursor, offs = [], 0, []
+    for i in range(num_blocks):
+        bt = tc_block_tensors(sd, net_prefix, i, update_pos, with_backward)
+        row = []
+        for name in TC_SLOTS:
+            if name not in bt:
+                row.append(-1)
+                continue
+            img = tc_image(bt[name])
+            pad = (-img.numel()) % 64                          # int16 elements -> 128 bytes
+            row.append(cursor * 2)
+            chunks.append(img)
+            if pad:
+                chunks.append(torch.zeros(pad, dtype=torch.int16))
+            cursor += img.numel() + pad
+        offs.append(row)
+    return torch.cat(chunks), offs

@@ -39,7 +39,9 @@ def test_library_loaded_and_counts_launches(gpu_models, dev):
     from moldiff_b200 import engine
     before = engine.launch_count()
     cuda_moldiff(gpu_models[0], batch_inputs(B=2), dev)
-    assert engine.launch_count() - before == 2 + 1 + 3 * 6 + 1   # init x2, pre(0), 3 per block, edge decode
+    tc = gpu_models[0]._packed_net(dev).tc_blob is not None
+    # init x2, pre(0), 3 per block (+1 tensor-core NodeBlock kernel per block), edge decode
+    assert engine.launch_count() - before == 2 + 1 + (4 if tc else 3) * 6 + 1
 
 
 @pytest.mark.parametrize("name", ["B4_mixed_t", "B4_pos3", "B32_t500"])
@@ -234,3 +236,16 @@ def test_guided_sample_step_runs(gpu_models, dev):
     preds = md.sample_step(st, 999, bond_predictor=bp, guidance=("uncertainty", 1e-4))
     assert torch.isfinite(st["pos"]).all() and not torch.equal(st["pos"], pos0)
     assert all(torch.isfinite(v).all() for v in preds.values())
+
+
+def test_fp32_ffma_path_still_matches(seeded_models, dev, monkeypatch):
+    """MDB_DISABLE_TC=1 keeps every layer on the fp32 FFMA kernels (the ~1e-6 parity mode)."""
+    import copy
+    monkeypatch.setenv("MDB_DISABLE_TC", "1")
+    model = copy.deepcopy(seeded_models[0]).to(dev).eval()
+    assert model._packed_net(dev).tc_blob is None
+    inp = batch_inputs(B=5, seed_graph=11, seed_inputs=12, t_values=(20, 480, 940))
+    ref = oracle_moldiff(seeded_models[0].state_dict(), inp)
+    out = cuda_moldiff(model, inp, dev)
+    for k in ref:
+        assert R.rel_err(out[k], ref[k]) < 2e-5, k
