@@ -849,7 +849,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
       LAUNCH(MDB_K_tc_nodeblock, st,
-             (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, tc::NTHREADS_TC, SMEM_TC_NB, st>>>(ta)));
+             (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
     }
     fill_blk(na.mid, net, i);
     na.do_mid = 1; na.do_pre = (i + 1 < L); na.do_dec = (i + 1 == L) && net->kind != 0;

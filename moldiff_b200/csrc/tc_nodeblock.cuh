@@ -26,69 +26,87 @@ struct TcNbArgs {
 };
 
 constexpr int OUT_LD = 260;   // fp32 row stride of the out tile in smem: 1040 B = 16 (mod 128) -> conflict-free rows
+constexpr int TC_NRW = 8;     // row warps: thread (w, t) owns row 32 * (w % 4) + t, columns [128 * (w / 4), +128)
+constexpr int TC_NB_THREADS = (TC_NRW + 2) * 32;
 
 // Row-thread helpers ------------------------------------------------------------------------------------------
-// mean / rstd of (acc[lane row][0:256] + bias[0:256] (+ extra row)) with two TMEM passes (two-pass variance).
-template <bool HAS_EXTRA>
-__device__ __forceinline__ void row_ln_stats(uint32_t taddr, const float* __restrict__ bias,
-                                             const float* __restrict__ extra, float& mean, float& rstd) {
+// v[0:128] <- this thread's half row of the accumulator (TMEM lane = row, columns taddr .. +128): four 32-column
+// loads in flight, one wait.
+__device__ __forceinline__ void load_half_row(uint32_t taddr, float (&v)[128]) {
+  uint32_t r0[32], r1[32], r2[32], r3[32];
+  tc::tmem_ld32_issue(taddr, r0);
+  tc::tmem_ld32_issue(taddr + 32, r1);
+  tc::tmem_ld32_issue(taddr + 64, r2);
+  tc::tmem_ld32_issue(taddr + 96, r3);
+  tc::tmem_ld32_wait(r0); tc::tmem_ld32_wait(r1); tc::tmem_ld32_wait(r2); tc::tmem_ld32_wait(r3);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]);
+    v[64 + i] = __uint_as_float(r2[i]); v[96 + i] = __uint_as_float(r3[i]);
+  }
+}
+
+// v += vec[0:128]  (vec: global, identical for every thread of the warp -> broadcast loads)
+__device__ __forceinline__ void add_vec128(float (&v)[128], const float* __restrict__ vec) {
+#pragma unroll
+  for (int i = 0; i < 128; i += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(vec + i));
+    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  }
+}
+// v += row[0:128]  (row: this thread's own gathered table row)
+__device__ __forceinline__ void add_row128(float (&v)[128], const float* __restrict__ row) {
+#pragma unroll
+  for (int i = 0; i < 128; i += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(row + i);
+    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+  }
+}
+
+// LayerNorm over the full 256-wide row whose two halves live in two threads: each half computes (mean, M2) of its
+// 128 values two-pass, the halves are merged exactly (Chan et al.) through `stat`, then v <- relu(LN(v) * g + b).
+__device__ __forceinline__ void ln_relu_half(float (&v)[128], const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, float2* stat, int row, int half) {
   float s = 0.f;
-  for (int c0 = 0; c0 < 256; c0 += 32) {
-    float v[32];
-    tc::tmem_ld32(taddr + c0, v);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (HAS_EXTRA) x = *reinterpret_cast<const float4*>(extra + c0 + i);
-      s += (v[i] + b.x + x.x) + (v[i + 1] + b.y + x.y) + (v[i + 2] + b.z + x.z) + (v[i + 3] + b.w + x.w);
-    }
-  }
-  mean = s * (1.f / 256.f);
+  for (int i = 0; i < 128; ++i) s += v[i];
+  const float m_h = s * (1.f / 128.f);
   float q = 0.f;
-  for (int c0 = 0; c0 < 256; c0 += 32) {
-    float v[32];
-    tc::tmem_ld32(taddr + c0, v);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (HAS_EXTRA) x = *reinterpret_cast<const float4*>(extra + c0 + i);
-      const float d0 = v[i] + b.x + x.x - mean, d1 = v[i + 1] + b.y + x.y - mean;
-      const float d2 = v[i + 2] + b.z + x.z - mean, d3 = v[i + 3] + b.w + x.w - mean;
-      q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
-    }
-  }
-  rstd = 1.f / sqrtf(q * (1.f / 256.f) + LN_EPS);
-}
-
-// A planes (K = 256) <- relu(LN(acc + bias (+ extra)) * gamma + beta), row `r`.
-template <bool HAS_EXTRA>
-__device__ __forceinline__ void row_ln_relu_to_a(uint32_t taddr, const float* __restrict__ bias,
-                                                 const float* __restrict__ extra, const float* __restrict__ gamma,
-                                                 const float* __restrict__ beta, uint8_t* a_hi, uint8_t* a_lo, int r) {
-  float mean, rstd;
-  row_ln_stats<HAS_EXTRA>(taddr, bias, extra, mean, rstd);
-  for (int c0 = 0; c0 < 256; c0 += 32) {
-    float v[32];
-    tc::tmem_ld32(taddr + c0, v);
+  for (int i = 0; i < 128; ++i) { const float d = v[i] - m_h; q = fmaf(d, d, q); }
+  stat[half * tc::ROWS + row] = make_float2(m_h, q);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float2 o = stat[(half ^ 1) * tc::ROWS + row];
+  const float mean = 0.5f * (m_h + o.x);
+  const float dm = m_h - o.x;
+  const float rstd = 1.f / sqrtf((q + o.y + dm * dm * 64.f) * (1.f / 256.f) + LN_EPS);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float4 b = bias ? __ldg(reinterpret_cast<const float4*>(bias + c0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0 + i));
-      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c0 + i));
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (HAS_EXTRA) x = *reinterpret_cast<const float4*>(extra + c0 + i);
-      v[i] = fmaxf((v[i] + b.x + x.x - mean) * rstd * g.x + be.x, 0.f);
-      v[i + 1] = fmaxf((v[i + 1] + b.y + x.y - mean) * rstd * g.y + be.y, 0.f);
-      v[i + 2] = fmaxf((v[i + 2] + b.z + x.z - mean) * rstd * g.z + be.z, 0.f);
-      v[i + 3] = fmaxf((v[i + 3] + b.w + x.w - mean) * rstd * g.w + be.w, 0.f);
-    }
-    tc::store_a32<256>(a_hi, a_lo, r, c0, v);
+  for (int i = 0; i < 128; i += 4) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
+    v[i] = fmaxf((v[i] - mean) * rstd * g.x + b.x, 0.f);
+    v[i + 1] = fmaxf((v[i + 1] - mean) * rstd * g.y + b.y, 0.f);
+    v[i + 2] = fmaxf((v[i + 2] - mean) * rstd * g.z + b.z, 0.f);
+    v[i + 3] = fmaxf((v[i + 3] - mean) * rstd * g.w + b.w, 0.f);
   }
 }
 
-__global__ void __launch_bounds__(tc::NTHREADS_TC, 1) tc_nodeblock_fwd_kernel(const TcNbArgs a) {
+// this thread's 128 values -> columns [k0, k0 + 128) of row r of the K = 256 A planes
+__device__ __forceinline__ void store_half_row_a(uint8_t* a_hi, uint8_t* a_lo, int r, int k0, const float (&v)[128]) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = v[c * 8 + i];
+    uint4 hi, lo;
+    tc::split8(x, hi, lo);
+    const uint32_t off = tc::a_chunk_off<256>(r, k0 / 8 + c);
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(const TcNbArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* e_hi = smem_raw;                               // 128 x 64 bf16 = 16 KB
   uint8_t* e_lo = e_hi + tc::ROWS * C * 2;
@@ -96,23 +114,26 @@ __global__ void __launch_bounds__(tc::NTHREADS_TC, 1) tc_nodeblock_fwd_kernel(co
   uint8_t* x_lo = x_hi + tc::ROWS * D * 2;
   uint8_t* stages = x_lo + tc::ROWS * D * 2;              // 2 x 32 KB
   tc::PipeSmem* ps = reinterpret_cast<tc::PipeSmem*>(stages + tc::NSTAGE * tc::STAGE_SLOT);
-  int* ls = reinterpret_cast<int*>(ps + 1);
-  int* rs = ls + tc::ROWS;
+  float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 64);     // [2][128]
+  int* ls = reinterpret_cast<int*>(stat + 2 * tc::ROWS);
   float* out_tile = reinterpret_cast<float*>(smem_raw);   // [128][OUT_LD] fp32, aliases the E and X planes at the end
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * tc::ROWS;
   const float* blob = a.blob;
   const BlkOff& off = a.off;
   const Tables& tb = a.tb;
   tc::Pipe p;
-  tc::pipe_init(p, ps, stages);
-  if (warp == 4) tc::tmem_alloc<512>(&ps->tmem_base);
-  int my_l = -1, my_r = -1;
+  tc::pipe_init<TC_NRW>(p, ps, stages);
+  if (warp == TC_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
+  const int row = (warp & 3) * 32 + lane;    // meaningful for row threads
+  const int half = (warp >> 2) & 1;
+  const int hc = half * 128;                 // first column of this thread's half
+  int my_r = -1;
   if (p.role == 0) {
-    const int q = q0 + tid;
-    if (q < a.n_edges) { my_l = a.left[q]; my_r = a.right[q]; }
-    ls[tid] = my_l; rs[tid] = my_r;
+    const int q = q0 + row;
+    if (q < a.n_edges) { my_r = a.right[q]; if (half == 0) ls[row] = a.left[q]; }
+    else if (half == 0) ls[row] = -1;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -121,54 +142,62 @@ __global__ void __launch_bounds__(tc::NTHREADS_TC, 1) tc_nodeblock_fwd_kernel(co
   const uint32_t D0 = 0, D1 = 256;          // TMEM column bases: msg accumulator / everything else
   const int rr = my_r < 0 ? 0 : my_r;
 
-  // ---- rows: e tile -> E planes
+  // ---- rows: e tile -> E planes (each thread 32 of the 64 columns of its row)
   if (p.role == 0) {
-    const int q = q0 + tid;
-    for (int k0 = 0; k0 < C; k0 += 32) {
-      float v[32];
+    const int q = q0 + row;
+    const int k0 = half * 32;
+    float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q < a.n_edges) x = *reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C + k0 + i);
-        v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
-      }
-      tc::store_a32<C>(e_hi, e_lo, tid, k0, v);
+    for (int i = 0; i < 32; i += 4) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < a.n_edges) x = *reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C + k0 + i);
+      v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
     }
+    tc::store_a32<C>(e_hi, e_lo, row, k0, v);
     tc::rows_publish(p);
   }
   // G1: edge_net.net.0                                                            graph.py:42
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), D1, false, true, true);
   if (p.role == 0) {
     tc::rows_wait_acc(p);
-    row_ln_relu_to_a<false>(lane_base + D1, W_(NB_EN1_B), nullptr, W_(NB_EN1_G), W_(NB_EN1_BE), x_hi, x_lo, tid);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_vec128(v, W_(NB_EN1_B) + hc);
+    ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
+    store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
   }
   // G2: edge_net.net.3 ; m = he * node_net(x)[col]                               graph.py:43
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_EN2), D1, false, true, true);
   if (p.role == 0) {
-    tc::rows_wait_acc(p);
-    const float* hn = tb.hn + (size_t)rr * D;
-    const float* b2 = W_(NB_EN2_B);
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      float v[32];
-      tc::tmem_ld32(lane_base + D1 + c0, v);
+    const float* hn = tb.hn + (size_t)rr * D + hc;          // gathered row: pull it into L1 while the MMAs run
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + c0 + i));
-        const float4 h = *reinterpret_cast<const float4*>(hn + c0 + i);
-        v[i] = (v[i] + b.x) * h.x; v[i + 1] = (v[i + 1] + b.y) * h.y;
-        v[i + 2] = (v[i + 2] + b.z) * h.z; v[i + 3] = (v[i + 3] + b.w) * h.w;
-      }
-      tc::store_a32<D>(x_hi, x_lo, tid, c0, v);
+    for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(hn + i));
+    tc::rows_wait_acc(p);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_vec128(v, W_(NB_EN2_B) + hc);
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(hn + i);
+      v[i] *= t4.x; v[i + 1] *= t4.y; v[i + 2] *= t4.z; v[i + 3] *= t4.w;
     }
+    store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
   }
   // G3: msg_net -> D0 (stays in TMEM) ; G4: gate.net.0 edge columns -> D1         graph.py:43,46
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_MSG), D0, false, true, false);
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), D1, false, false, true);
   if (p.role == 0) {
+    const float* gxr = tb.gx + (size_t)rr * D + hc;
+#pragma unroll
+    for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(gxr + i));
     tc::rows_wait_acc(p);
-    row_ln_relu_to_a<true>(lane_base + D1, nullptr, tb.gx + (size_t)rr * D, W_(NB_G1_G), W_(NB_G1_BE), x_hi, x_lo, tid);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_row128(v, gxr);                                    // hoisted node / time / bias part of gate.net.0
+    ln_relu_half(v, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, stat, row, half);
+    store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
   }
   // G5: gate.net.3                                                                graph.py:46
@@ -176,46 +205,46 @@ __global__ void __launch_bounds__(tc::NTHREADS_TC, 1) tc_nodeblock_fwd_kernel(co
   if (p.role == 0) {
     tc::rows_wait_acc(p);
     // out = (msg + b) * sigmoid(gate + b)  -> smem tile (all operand planes are dead now)     graph.py:47
-    const float* bm = W_(NB_MSG_B);
-    const float* bg = W_(NB_G2_B);
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      float m[32], g[32];
-      tc::tmem_ld32(lane_base + D0 + c0, m);
-      tc::tmem_ld32(lane_base + D1 + c0, g);
+    {
+      float v[128];
+      load_half_row(lane_base + D1 + hc, v);
+      add_vec128(v, W_(NB_G2_B) + hc);
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bm + c0 + i));
-        const float4 b2 = __ldg(reinterpret_cast<const float4*>(bg + c0 + i));
-        float4 o;
-        o.x = (m[i] + b1.x) * (1.f / (1.f + expf(-(g[i] + b2.x))));
-        o.y = (m[i + 1] + b1.y) * (1.f / (1.f + expf(-(g[i + 1] + b2.y))));
-        o.z = (m[i + 2] + b1.z) * (1.f / (1.f + expf(-(g[i + 2] + b2.z))));
-        o.w = (m[i + 3] + b1.w) * (1.f / (1.f + expf(-(g[i + 3] + b2.w))));
-        *reinterpret_cast<float4*>(out_tile + tid * OUT_LD + c0 + i) = o;
+      for (int i = 0; i < 128; i += 4)                    // park sigmoid(gate) in the tile, then fold msg in
+        *reinterpret_cast<float4*>(out_tile + row * OUT_LD + hc + i) =
+            make_float4(1.f / (1.f + expf(-v[i])), 1.f / (1.f + expf(-v[i + 1])), 1.f / (1.f + expf(-v[i + 2])),
+                        1.f / (1.f + expf(-v[i + 3])));
+      load_half_row(lane_base + D0 + hc, v);
+      add_vec128(v, W_(NB_MSG_B) + hc);
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        float4* o = reinterpret_cast<float4*>(out_tile + row * OUT_LD + hc + i);
+        const float4 g = *o;
+        *o = make_float4(v[i] * g.x, v[i + 1] * g.y, v[i + 2] * g.z, v[i + 3] * g.w);
       }
     }
     tc::fence_before_sync();
-    asm volatile("bar.sync 1, 128;" ::: "memory");      // row threads only
-    // scatter_sum over row (= left): thread c owns channels c and c + 128, walks the 128 CSR-ordered rows   graph.py:50
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // row threads only
+    // scatter_sum over row (= left): thread c owns channel c and walks the 128 CSR-ordered rows       graph.py:50
     int cur = ls[0];
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f;
     for (int r = 0; r < tc::ROWS; ++r) {
       const int n = ls[r];
       if (n != cur) {
-        if (cur >= 0) { atomicAdd(tb.agg + (size_t)cur * D + tid, s0); atomicAdd(tb.agg + (size_t)cur * D + tid + 128, s1); }
-        cur = n; s0 = 0.f; s1 = 0.f;
+        if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + tid, s0);
+        cur = n; s0 = 0.f;
       }
       s0 += out_tile[r * OUT_LD + tid];
-      s1 += out_tile[r * OUT_LD + tid + 128];
     }
-    if (cur >= 0) { atomicAdd(tb.agg + (size_t)cur * D + tid, s0); atomicAdd(tb.agg + (size_t)cur * D + tid + 128, s1); }
+    if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + tid, s0);
   }
   __syncthreads();
-  if (warp == 4) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
+  if (warp == TC_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
 }
 
 constexpr size_t SMEM_TC_NB = 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2 + tc::NSTAGE * tc::STAGE_SLOT
-                              + sizeof(tc::PipeSmem) + 2 * tc::ROWS * sizeof(int) + 64;
+                              + 64 + 2 * tc::ROWS * sizeof(float2) + tc::ROWS * sizeof(int) + 64;
+static_assert(sizeof(tc::PipeSmem) <= 64, "PipeSmem must fit its 64-byte slot");
 static_assert(SMEM_TC_NB <= 232448, "tc_nodeblock_fwd_kernel exceeds the 227 KB shared-memory limit");
 static_assert((size_t)tc::ROWS * OUT_LD * 4 <= 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2,
               "out tile must fit in the operand planes it aliases");

@@ -1,8 +1,9 @@
 // Warp-specialised GEMM pipeline on top of tc_engine.cuh, shared by every tensor-core kernel of the path.
 //
-// CTA = 6 warps: warps 0-3 are the 128 "row" threads (thread t owns tile row t = TMEM lane t: they build the A
-// operand, and run every epilogue from TMEM), warp 4 lane 0 streams weight stages L2 -> smem with cp.async.bulk,
-// warp 5 lane 0 issues tcgen05.mma.  All three roles walk the same static sequence of GEMMs; they meet only on
+// CTA = NRW row warps + 2: the row warps (4 or 8) build the A operand and run every epilogue from TMEM (thread t
+// of warp w owns tile row 32 * (w % 4) + t = its TMEM lane; with 8 row warps, warps 4-7 take the upper half of
+// the columns of the same rows), lane 0 of the next warp streams weight stages L2 -> smem with cp.async.bulk,
+// lane 0 of the last warp issues tcgen05.mma.  All three roles walk the same static sequence of GEMMs; they meet only on
 // mbarriers:
 //     a_ready (128 arrivals)  rows -> MMA   "A planes written, previous accumulator drained"
 //     full[s] / empty[s]      producer <-> MMA, one weight stage each (empty is signalled by tcgen05.commit)
@@ -33,14 +34,15 @@ struct Pipe {
   int role;             // 0 = row thread, 1 = producer thread, 2 = MMA thread, 3 = idle lane
 };
 
+template <int NRW = 4>   // number of row warps (4: one thread per row; 8: two threads per row, split by column half)
 __device__ __forceinline__ void pipe_init(Pipe& p, PipeSmem* s, uint8_t* stages) {
   p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  p.role = warp < 4 ? 0 : (lane == 0 ? (warp == 4 ? 1 : 2) : 3);
+  p.role = warp < NRW ? 0 : (lane == 0 ? (warp == NRW ? 1 : 2) : 3);
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&s->full[i], 1); mbar_init(&s->empty[i], 1); }
     mbar_init(&s->done, 1);
-    mbar_init(&s->a_ready, ROWS);
+    mbar_init(&s->a_ready, NRW * 32);
     fence_barrier_init();
   }
 }
