@@ -248,3 +248,323 @@ static_assert(sizeof(tc::PipeSmem) <= 64, "PipeSmem must fit its 64-byte slot");
 static_assert(SMEM_TC_NB <= 232448, "tc_nodeblock_fwd_kernel exceeds the 227 KB shared-memory limit");
 static_assert((size_t)tc::ROWS * OUT_LD * 4 <= 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2,
               "out tile must fit in the operand planes it aliases");
+
+// =================================================================================================================
+// Backward of the NodeBlock per-edge path on tensor cores (same math as bwd_edge_nodeblock_kernel in mdb_backward.cuh)
+// =================================================================================================================
+struct TcNbBwdArgs {
+  const float* blob;
+  const uint8_t* tc_blob;
+  BlkOff off;
+  TcOff tco;
+  Tables tb;
+  const int *left, *right;
+  int n_nodes, n_edges;
+  const float* e;        // [E][64] saved e_i
+  const float* dagg;     // [N][256] d/d (aggregated messages)
+  float *dgx, *dhn;      // [N][256] scatter targets (pre-zeroed)
+  float* de;             // [E][64]  d/d e, accumulated (+=)
+};
+
+// cross-half exchange of two partial values per row; returns the partner's pair
+__device__ __forceinline__ float2 exchange_half(float2* stat, int row, int half, float x, float y) {
+  stat[half * tc::ROWS + row] = make_float2(x, y);
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  const float2 o = stat[(half ^ 1) * tc::ROWS + row];
+  asm volatile("bar.sync 1, 256;" ::: "memory");     // the buffer may be rewritten right after
+  return o;
+}
+
+// d (in: gradient w.r.t. relu(LN(a) * g + b) for this thread's 128 columns; out: gradient w.r.t. a), where the
+// pre-LayerNorm activations a = acc (TMEM, columns taddr..+128) + bias (optional) + extra row (optional) are
+// re-read from the accumulator chunk by chunk instead of being stored.
+template <bool HAS_BIAS, bool HAS_EXTRA>
+__device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ extra,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            float (&d)[128], float2* stat, int row, int half) {
+  auto pre = [&](int c0, float (&a)[32]) {       // a <- pre-LN activations of columns [c0, c0 + 32)
+    tc::tmem_ld32(taddr + c0, a);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (HAS_BIAS) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+        a[i] += b.x; a[i + 1] += b.y; a[i + 2] += b.z; a[i + 3] += b.w;
+      }
+      if (HAS_EXTRA) {
+        const float4 x = *reinterpret_cast<const float4*>(extra + c0 + i);
+        a[i] += x.x; a[i + 1] += x.y; a[i + 2] += x.z; a[i + 3] += x.w;
+      }
+    }
+  };
+  float s = 0.f;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    float a[32];
+    pre(c0, a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += a[i];
+  }
+  const float m_h = s * (1.f / 128.f);
+  float q = 0.f;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    float a[32];
+    pre(c0, a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float t = a[i] - m_h; q = fmaf(t, t, q); }
+  }
+  const float2 o = exchange_half(stat, row, half, m_h, q);
+  const float mean = 0.5f * (m_h + o.x);
+  const float dm = m_h - o.x;
+  const float rstd = 1.f / sqrtf((q + o.y + dm * dm * 64.f) * (1.f / 256.f) + LN_EPS);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    float a[32];
+    pre(cc * 32, a);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + cc * 32 + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + cc * 32 + i));
+      const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float xh = (a[i + u] - mean) * rstd;
+        const float dxh = (xh * gg[u] + bb[u] > 0.f) ? d[cc * 32 + i + u] * gg[u] : 0.f;
+        d[cc * 32 + i + u] = dxh;
+        s1 += dxh;
+        s2 = fmaf(dxh, xh, s2);
+      }
+    }
+  }
+  const float2 o2 = exchange_half(stat, row, half, s1, s2);
+  const float m1 = (s1 + o2.x) * (1.f / 256.f), m2 = (s2 + o2.y) * (1.f / 256.f);
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    float a[32];
+    pre(cc * 32, a);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float xh = (a[i] - mean) * rstd;
+      d[cc * 32 + i] = rstd * (d[cc * 32 + i] - m1 - xh * m2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(const TcNbBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* e_hi = smem_raw;
+  uint8_t* e_lo = e_hi + tc::ROWS * C * 2;
+  uint8_t* x_hi = e_lo + tc::ROWS * C * 2;
+  uint8_t* x_lo = x_hi + tc::ROWS * D * 2;
+  uint8_t* stages = x_lo + tc::ROWS * D * 2;
+  tc::PipeSmem* ps = reinterpret_cast<tc::PipeSmem*>(stages + tc::NSTAGE * tc::STAGE_SLOT);
+  float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * tc::ROWS;
+  const float* blob = a.blob;
+  const BlkOff& off = a.off;
+  const Tables& tb = a.tb;
+  tc::Pipe p;
+  tc::pipe_init<TC_NRW>(p, ps, stages);
+  if (warp == TC_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
+  const int row = (warp & 3) * 32 + lane;
+  const int half = (warp >> 2) & 1;
+  const int hc = half * 128;
+  const int dc = half * 32;                   // this thread's 32 of the 64 d/d e columns
+  const int q = q0 + row;
+  const bool valid = p.role == 0 && q < a.n_edges;
+  const int ll = valid ? a.left[q] : 0, rr = valid ? a.right[q] : 0;
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t D0 = 0, D1 = 256;
+  const float* hn = tb.hn + (size_t)rr * D + hc;
+  const float* gxr = tb.gx + (size_t)rr * D + hc;
+  float de[32];
+
+  if (p.role == 0) {   // e tile -> E planes
+    const int k0 = half * 32;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) x = *reinterpret_cast<const float4*>(a.e + (size_t)q * C + k0 + i);
+      v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+    }
+    tc::store_a32<C>(e_hi, e_lo, row, k0, v);
+    tc::rows_publish(p);
+  }
+  // ---- forward recompute up to msg (D0) and sigmoid(gate)
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), D1, false, true, true);
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_vec128(v, W_(NB_EN1_B) + hc);
+    ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
+    store_half_row_a(x_hi, x_lo, row, hc, v);
+    tc::rows_publish(p);
+  }
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_EN2), D1, false, true, true);
+  if (p.role == 0) {
+#pragma unroll
+    for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(hn + i));
+    tc::rows_wait_acc(p);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_vec128(v, W_(NB_EN2_B) + hc);
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(hn + i);
+      v[i] *= t4.x; v[i + 1] *= t4.y; v[i + 2] *= t4.z; v[i + 3] *= t4.w;
+    }
+    store_half_row_a(x_hi, x_lo, row, hc, v);
+    tc::rows_publish(p);
+  }
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_MSG), D0, false, true, false);
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), D1, false, false, true);
+  if (p.role == 0) {
+#pragma unroll
+    for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(gxr + i));
+    tc::rows_wait_acc(p);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_row128(v, gxr);
+    ln_relu_half(v, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, stat, row, half);
+    store_half_row_a(x_hi, x_lo, row, hc, v);
+    tc::rows_publish(p);
+  }
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_G2), D1, false, true, true);
+  // ---- d out = dagg[l]:  d gate-logit -> X planes (A operand of the next GEMM),  d msg -> parked in D0 over msg
+  if (p.role == 0) {
+    const float* dout = a.dagg + (size_t)ll * D + hc;
+#pragma unroll
+    for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(dout + i));
+    tc::rows_wait_acc(p);
+    float sg[128];
+    load_half_row(lane_base + D1 + hc, sg);
+    add_vec128(sg, W_(NB_G2_B) + hc);
+#pragma unroll
+    for (int i = 0; i < 128; ++i) sg[i] = 1.f / (1.f + expf(-sg[i]));
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      float m[32];
+      tc::tmem_ld32(lane_base + D0 + hc + cc * 32, m);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(W_(NB_MSG_B) + hc + cc * 32 + i));
+        float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) dz = *reinterpret_cast<const float4*>(dout + cc * 32 + i);
+        const float bb[4] = {b.x, b.y, b.z, b.w}, dd[4] = {dz.x, dz.y, dz.z, dz.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float s = sg[cc * 32 + i + u];
+          const float msg = m[i + u] + bb[u];
+          m[i + u] = dd[u] * s;                                 // d msg
+          sg[cc * 32 + i + u] = dd[u] * msg * s * (1.f - s);    // d gate logit
+        }
+      }
+      tc::tmem_st32(lane_base + D0 + hc + cc * 32, m);
+    }
+    tc::tmem_st_wait();
+    store_half_row_a(x_hi, x_lo, row, hc, sg);
+    tc::rows_publish(p);
+  }
+  // ---- gate branch: d relu3 = d gt W_g2^T ; LN backward needs a3 again -> recompute into D1 after draining it
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(BT_NB_G2), D1, false, true, true);
+  float dr[128];
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    load_half_row(lane_base + D1 + hc, dr);
+    tc::rows_publish(p);
+  }
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), D1, false, true, true);
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    ln_bwd_half<false, true>(lane_base + D1 + hc, nullptr, gxr, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, dr, stat, row, half);
+    if (valid) {
+      float* dst = a.dgx + (size_t)rr * D + hc;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) tc::red_add_v4(dst + i, dr[i], dr[i + 1], dr[i + 2], dr[i + 3]);
+    }
+    store_half_row_a(x_hi, x_lo, row, hc, dr);
+    tc::rows_publish(p);
+  }
+  tc::gemm<D, C>(p, x_hi, x_lo, TCW_(BT_NB_GE), D1, false, true, true);      // d e (gate part) -> D1[0:64]
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    tc::tmem_ld32(lane_base + D1 + dc, de);
+    // d msg: D0 -> X planes
+    load_half_row(lane_base + D0 + hc, dr);
+    store_half_row_a(x_hi, x_lo, row, hc, dr);
+    tc::rows_publish(p);
+  }
+  // ---- message branch: dm = d msg W_msg^T -> D0 ; he needed again -> recompute (a2 -> r2 -> he) through D1
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(BT_NB_MSG), D0, false, true, false);
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), D1, false, false, true);
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    float v[128];
+    load_half_row(lane_base + D1 + hc, v);
+    add_vec128(v, W_(NB_EN1_B) + hc);
+    ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
+    store_half_row_a(x_hi, x_lo, row, hc, v);
+    tc::rows_publish(p);
+  }
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_EN2), D1, false, true, true);         // he
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    float* dst = a.dhn + (size_t)rr * D + hc;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      float he[32], dm[32];
+      tc::tmem_ld32(lane_base + D1 + hc + cc * 32, he);
+      tc::tmem_ld32(lane_base + D0 + hc + cc * 32, dm);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(W_(NB_EN2_B) + hc + cc * 32 + i));
+        const float4 h = *reinterpret_cast<const float4*>(hn + cc * 32 + i);
+        if (valid)
+          tc::red_add_v4(dst + cc * 32 + i, dm[i] * (he[i] + b.x), dm[i + 1] * (he[i + 1] + b.y),
+                         dm[i + 2] * (he[i + 2] + b.z), dm[i + 3] * (he[i + 3] + b.w));
+        dm[i] *= h.x; dm[i + 1] *= h.y; dm[i + 2] *= h.z; dm[i + 3] *= h.w;       // d he
+      }
+      tc::store_a32<D>(x_hi, x_lo, row, hc + cc * 32, dm);
+    }
+    tc::rows_publish(p);
+  }
+  // d relu2 = d he W_en2^T -> D1 ; a2 recompute -> D0 (dm is dead) ; one epilogue for both
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(BT_NB_EN2), D1, false, true, false);
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), D0, false, false, true);
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    load_half_row(lane_base + D1 + hc, dr);
+    ln_bwd_half<true, false>(lane_base + D0 + hc, W_(NB_EN1_B) + hc, nullptr, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc,
+                             dr, stat, row, half);
+    store_half_row_a(x_hi, x_lo, row, hc, dr);
+    tc::rows_publish(p);
+  }
+  tc::gemm<D, C>(p, x_hi, x_lo, TCW_(BT_NB_EN1), D1, false, true, true);       // d e (message part) -> D1[0:64]
+  if (p.role == 0) {
+    tc::rows_wait_acc(p);
+    float v[32];
+    tc::tmem_ld32(lane_base + D1 + dc, v);
+    if (valid) {
+      float* dst = a.de + (size_t)q * C + dc;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 o = *reinterpret_cast<float4*>(dst + i);
+        o.x += de[i] + v[i]; o.y += de[i + 1] + v[i + 1]; o.z += de[i + 2] + v[i + 2]; o.w += de[i + 3] + v[i + 3];
+        *reinterpret_cast<float4*>(dst + i) = o;
+      }
+    }
+    tc::fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == TC_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
+}
+
+constexpr size_t SMEM_TC_NB_BWD = 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2
+                                  + tc::NSTAGE * tc::STAGE_SLOT + 64 + 2 * tc::ROWS * sizeof(float2) + 64;
+static_assert(SMEM_TC_NB_BWD <= 232448, "tc_nodeblock_bwd_kernel exceeds the 227 KB shared-memory limit");
