@@ -279,16 +279,14 @@ def main():
                 "share_of_step": info["ms_total"] / max(sum(v["ms_total"] for v in prof.values()), 1e-9),
                 "per_kernel_ms": {k: round(v["ms_total"] / 3, 4) for k, v in prof.items()}}
 
-    # ---- end-of-run gather of the sampled molecules (the only collective of the path) ----
+    # ---- end-of-run gather of the sampled molecules (the only collective of the path; outside the timed region) ----
     if dist is not None:
-        sizes = torch.tensor([N, Eh], device=dev)
-        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
-        dist.all_gather(all_sizes, sizes)
-        maxn = max(int(s[0]) for s in all_sizes)
-        buf = torch.zeros(maxn, 3, device=dev)
-        buf[:N] = st["pos"]
-        out = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, out, dst=0)
+        from moldiff_b200.sharding import gather_predictions
+        last = step(0)
+        got = gather_predictions([last["pred_node"], last["pred_pos"], last["pred_halfedge"]],
+                                 d["batch_node"], d["batch_halfedge"], dist, dst=0)
+        if rank == 0:
+            assert got["n_graphs"] == total_mols
         dist.barrier()
 
     if rank == 0:

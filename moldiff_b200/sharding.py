@@ -1,0 +1,58 @@
+"""Molecule sharding across ranks (data parallel over independent molecules) and the end-of-run gather.
+
+Molecules never interact (edges are intra-molecule only; reference utils/transforms.py:136-141), so the T-step
+loop needs no collective at all: rank r samples its own molecules, and one variable-length gather to rank 0 at the
+end returns the predictions in the global molecule order.  Works with any torch.distributed backend (NCCL over
+NVLink on the 8 x B200 box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+
+
+def shard_sizes(n_graphs, world_size):
+    """Molecules per rank: as even as possible, earlier ranks take the remainder."""
+    base, rem = divmod(n_graphs, world_size)
+    return [base + (1 if r < rem else 0) for r in range(world_size)]
+
+
+def shard_range(n_graphs, rank, world_size):
+    sizes = shard_sizes(n_graphs, world_size)
+    start = sum(sizes[:rank])
+    return start, start + sizes[rank]
+
+
+def gather_predictions(pred, batch_node, batch_halfedge, dist, dst=0):
+    """pred = [pred_node [N_r, Kn], pred_pos [N_r, 3], pred_halfedge [Eh_r, Ke]] of this rank's molecules.
+    Returns on rank `dst` the concatenation over ranks (molecule ids renumbered globally), None elsewhere."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = pred[1].device
+    n_mol = int(batch_node.max()) + 1 if batch_node.numel() else 0
+    sizes = torch.tensor([pred[0].shape[0], pred[2].shape[0], n_mol], device=dev, dtype=torch.int64)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [s.tolist() for s in all_sizes]
+    max_n, max_e = max(s[0] for s in all_sizes), max(s[1] for s in all_sizes)
+
+    def pad(x, n):
+        out = torch.zeros((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev)
+        out[: x.shape[0]] = x
+        return out
+
+    payload = [pad(pred[0], max_n), pad(pred[1], max_n), pad(pred[2], max_e),
+               pad(batch_node.to(dev), max_n), pad(batch_halfedge.to(dev), max_e)]
+    gathered = []
+    for x in payload:
+        bufs = [torch.zeros_like(x) for _ in range(world)] if rank == dst else None
+        dist.gather(x, bufs, dst=dst)
+        gathered.append(bufs)
+    if rank != dst:
+        return None
+    out, mol0 = [[] for _ in range(5)], 0
+    for r in range(world):
+        n, e, m = all_sizes[r]
+        out[0].append(gathered[0][r][:n]); out[1].append(gathered[1][r][:n]); out[2].append(gathered[2][r][:e])
+        out[3].append(gathered[3][r][:n] + mol0); out[4].append(gathered[4][r][:e] + mol0)
+        mol0 += m
+    return {"pred": [torch.cat(out[0]), torch.cat(out[1]), torch.cat(out[2])],
+            "batch_node": torch.cat(out[3]), "batch_halfedge": torch.cat(out[4]), "n_graphs": mol0}

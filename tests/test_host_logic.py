@@ -1,0 +1,245 @@
+"""CPU: host-side logic of the product -- schedules, transitions, module tree / state_dict schema, the sampler's
+plumbing (with the oracle injected as the denoiser, tests only), sharding + gather under gloo world_size 2."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restatement as R
+from tests.helpers import batch_inputs, doubled
+
+
+def test_state_dict_schema_and_seeded_init_match_reference(golden, seeded_models):
+    md, bp = seeded_models
+    for model, keys, sums in ((md, golden["keys_moldiff"], golden["checksum_moldiff"]),
+                              (bp, golden["keys_bondpred"], golden["checksum_bondpred"])):
+        sd = model.state_dict()
+        assert set(sd) == set(keys)
+        for k, shape in keys.items():
+            assert tuple(sd[k].shape) == tuple(shape), k
+            s, a = sums[k]
+            assert float(sd[k].double().sum()) == s and float(sd[k].double().abs().sum()) == a, k
+    assert len(md.state_dict()) == 581 and len(bp.state_dict()) == 554
+
+
+def test_schedule_tables_match_reference(golden, seeded_models):
+    from moldiff_b200 import MolDiff
+    from moldiff_b200.config import builtin_config
+    torch.manual_seed(0)
+    simple = MolDiff(builtin_config("train/train_MolDiff_simple.yml").model, 8, 6)
+    sds = {"full": seeded_models[0].state_dict(), "simple": simple.state_dict(), "bond": seeded_models[1].state_dict()}
+    n = 0
+    for key, (idx, vals) in golden["schedules"].items():
+        tag, name = key.split("/", 1)
+        assert torch.equal(sds[tag][name][idx], vals), key      # bitwise: same float64 numpy arithmetic
+        n += 1
+    assert n >= 20
+
+
+def test_schedule_families():
+    from moldiff_b200.schedules import get_beta_schedule
+    for name, kw in (("linear", dict(beta_start=1e-4, beta_end=2e-2)), ("quad", dict(beta_start=1e-4, beta_end=2e-2)),
+                     ("const", dict(beta_end=0.01)), ("jsd", {}), ("sigmoid", dict(beta_start=1e-4, beta_end=2e-2)),
+                     ("cosine", {}), ("advance", dict(scale_start=0.9999, scale_end=1e-4, width=3))):
+        b = get_beta_schedule(name, 100, **kw)
+        assert b.shape == (100,) and np.all(b >= 0) and np.all(b <= 1)
+    with pytest.raises(NotImplementedError):
+        get_beta_schedule("nope", 10)
+    with pytest.raises(AssertionError):
+        get_beta_schedule("segment", 10, time_segment=[3, 3], segment_diff=[dict(scale_start=.9, scale_end=.5, width=2)] * 2)
+
+
+def test_transition_functions_match_reference(golden, seeded_models):
+    md = seeded_models[0]
+    tr = golden["transitions"]
+    i = tr["inputs"]
+    inp = batch_inputs(B=6, t_values=(999, 600, 599, 1, 0, 300))
+    bn, bh = inp["batch_node"], inp["batch_halfedge"]
+    with torch.no_grad():
+        torch.manual_seed(11)
+        assert torch.equal(md.pos_transition.get_prev_from_recon(i["x_t"], i["x0"], i["t"], bn), tr["pos_prev_seed11"])
+        assert torch.equal(md.edge_transition.q_v_posterior(i["log_v0"], i["log_vt"], i["t"], bh, v0_prob=True), tr["edge_post"])
+        assert torch.equal(md.node_transition.q_v_posterior(i["log_n0"], i["log_nt"], i["t"], bn, v0_prob=True), tr["node_post"])
+        assert torch.equal(md.edge_transition.q_vt_pred(i["log_vt"], i["t"], bh), tr["edge_qvt"])
+        # v0_prob=False branch: one-hot v0 must agree with the probability branch
+        oh = R.index_to_log_onehot(i["log_v0"].argmax(-1), 6)
+        a = md.edge_transition.q_v_posterior(oh, i["log_vt"], i["t"], bh, v0_prob=False)
+        b = md.edge_transition.q_v_posterior(oh, i["log_vt"], i["t"], bh, v0_prob=True)
+        assert torch.allclose(a, b, atol=1e-5)
+    cls, onehot, log_vt = md.node_transition.sample_init(1000)
+    assert onehot.shape == (1000, 8) and (cls == 7).float().mean() > 0.95          # 'tomask' start
+    assert md.edge_transition.sample_init(1000)[0].eq(0).float().mean() > 0.9      # 'absorb' start
+
+
+def test_add_noise_and_get_loss_plumbing(seeded_models, monkeypatch):
+    """get_loss / add_noise around an injected denoiser (the oracle): checks shapes, keys and finiteness."""
+    md = seeded_models[0]
+    sd = md.state_dict()
+
+    def oracle_forward(self, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t):
+        with torch.no_grad():
+            return R.moldiff_forward(sd, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t)
+
+    monkeypatch.setattr(type(md), "forward", oracle_forward)
+    inp = batch_inputs(B=3)
+    node_type, half_type = inp["h_node"].argmax(-1), inp["h_half"].argmax(-1).clamp_max(4)
+    torch.manual_seed(3)
+    out = md.get_loss(node_type, inp["pos"], inp["batch_node"], half_type, inp["halfedge_index"], inp["batch_halfedge"], 3)
+    assert set(out) == {"loss", "loss_pos", "loss_node", "loss_edge"} and all(torch.isfinite(v) for v in out.values())
+    h, p, e = md.add_noise(node_type, inp["pos"], inp["batch_node"], half_type, inp["halfedge_index"],
+                           inp["batch_halfedge"], 3, t=500)
+    assert h.shape == inp["h_node"].shape and p.shape == inp["pos"].shape and e.shape == inp["h_half"].shape
+
+
+def test_sampler_loop_reproduces_reference_trajectory(golden, monkeypatch):
+    """With the oracle injected as the denoiser and the same seeds, MolDiff.sample consumes the RNG in the same
+    order as the reference and so reproduces its 50-step CPU trajectory (final state and last predictions)."""
+    from moldiff_b200 import MolDiff
+    from moldiff_b200.config import builtin_config
+    cfg = builtin_config("train/train_MolDiff_simple.yml").model
+    cfg.diff.num_timesteps = 50
+    torch.manual_seed(0)
+    md = MolDiff(cfg, 8, 6).eval()
+    sd = md.state_dict()
+
+    def oracle_forward(self, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t):
+        with torch.no_grad():
+            return R.moldiff_forward(sd, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t,
+                                     num_timesteps=50)
+
+    monkeypatch.setattr(MolDiff, "forward", oracle_forward)
+    from moldiff_b200.placeholder import make_data_placeholder
+    np.random.seed(2023)
+    ph = make_data_placeholder(3)
+    torch.manual_seed(2023)
+    out = md.sample(3, ph["batch_node"], ph["halfedge_index"], ph["batch_halfedge"])
+    g = golden["sample50"]
+    assert out["traj"][0].shape[0] == 51
+    assert torch.equal(out["traj"][0][-1].argmax(-1), g["last_state"]["node"])
+    assert torch.equal(out["traj"][2][-1].argmax(-1), g["last_state"]["half"])
+    assert R.rel_err(out["traj"][1][-1], g["last_state"]["pos"]) < 1e-5
+    for a, b in zip(out["pred"], g["final_pred"]):
+        assert R.rel_err(a, b) < 1e-5
+    for i, st in g["steps"].items():               # the recorded per-step states are on our trajectory too
+        assert torch.equal(out["traj"][0][i], st["h_node"]) and R.rel_err(out["traj"][1][i], st["pos"]) < 1e-5
+
+
+def test_guidance_objectives_autograd_plumbing(seeded_models, monkeypatch):
+    """All nine guidance variants of model.py:317-361 run through _guidance_delta with a differentiable stand-in."""
+    md = seeded_models[0]
+    inp = batch_inputs(B=2)
+    ei, be, _ = doubled(inp)
+    nh = ei.shape[1] // 2
+    W = torch.randn(3, 5)
+
+    def fake_bond(h_node, pos, batch_node, edge_index, batch_edge, t):
+        d = (pos[edge_index[0, :nh]] - pos[edge_index[1, :nh]])
+        return d @ W
+    half_prev = torch.randint(0, 6, (nh,))
+    log_half = torch.log_softmax(torch.randn(nh, 6), -1)
+    for gui in ("entropy", "uncertainty", "uncertainty_bond", "entropy_bond", "logit_bond", "logit", "crossent", "crossent_bond"):
+        d = md._guidance_delta(fake_bond, gui, 1e-4, inp["h_node"], inp["pos"], inp["batch_node"], ei, be, inp["t"],
+                               half_prev, log_half)
+        assert d.shape == inp["pos"].shape and torch.isfinite(d).all(), gui
+    with pytest.raises(NotImplementedError):
+        md._guidance_delta(fake_bond, "nope", 1e-4, inp["h_node"], inp["pos"], inp["batch_node"], ei, be, inp["t"], half_prev, log_half)
+
+
+def test_config_surface():
+    from moldiff_b200.config import AttrDict, builtin_config
+    c = builtin_config("train/train_MolDiff.yml")
+    assert c.model.denoiser.num_blocks == 6 and c.model["diff"]["time_dim"] == 10
+    assert dict(**c.model.denoiser)["backbone"] == "NodeEdgeNet"             # **-splat like EasyDict
+    assert getattr(c.model, "bond_len_loss", False) is False
+    assert builtin_config("sample/sample_MolDiff.yml").sample.guidance == ["uncertainty", 1e-4]
+    assert isinstance(AttrDict({"a": {"b": 1}}).a, AttrDict)
+    from moldiff_b200 import NodeEdgeNet
+    with pytest.raises(NotImplementedError):
+        NodeEdgeNet(128, 64, num_blocks=2, cutoff=10, use_gate=True)          # kernels are specialised: loud, not silent
+
+
+def test_reference_module_paths():
+    import models.bond_predictor
+    import models.common
+    import models.diffusion
+    import models.graph
+    import models.model
+    import models.transition
+    from moldiff_b200 import BondPredictor, MolDiff, NodeEdgeNet
+    assert models.model.MolDiff is MolDiff and models.bond_predictor.BondPredictor is BondPredictor
+    assert models.graph.NodeEdgeNet is NodeEdgeNet
+    assert models.diffusion.extract(torch.arange(10.), torch.tensor([3, 5]), torch.tensor([0, 0, 1])).shape == (3, 1)
+
+
+def test_packing_roundtrip_and_tc_images(seeded_models):
+    from moldiff_b200 import packing
+    sd = seeded_models[0].state_dict()
+    blob, head_off, block_off = packing.pack_network(sd, kind=1, net_prefix="denoiser", num_blocks=6, update_pos=True, time_dim=10)
+    o = block_off[3][packing.BLOCK_SLOTS.index("NB_MSG_W")]
+    w = sd["denoiser.node_blocks_with_edge.3.msg_net.weight"]
+    assert torch.equal(blob[o:o + 256 * 256].reshape(256, 256), w.t())
+    assert all(x % 32 == 0 for row in block_off for x in row if x >= 0)           # 128-byte aligned slots
+    img = packing.tc_image(w.t().contiguous())
+    hi, lo = packing.split_bf16(w)                                                 # [N][K]
+    assert img.numel() == 2 * 256 * 256
+    # element (n, k) of stage s = k // 32 sits at (n%8)*8 + (n//8)*(32//8)*64 + ((k%32)//8)*64 + k%8  (int16 units)
+    n, k = 37, 170
+    s, kk = divmod(k, 32)
+    base = s * 2 * 256 * 32
+    idx = base + (n % 8) * 8 + (n // 8) * 4 * 64 + (kk // 8) * 64 + kk % 8
+    assert img[idx] == hi[n, k].view(torch.int16) and img[idx + 256 * 32] == lo[n, k].view(torch.int16)
+    tcb, tco = packing.pack_tc(sd, net_prefix="denoiser", num_blocks=6, update_pos=True, with_backward=False)
+    assert all(x % 128 == 0 for row in tco for x in row if x >= 0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n_graphs, q):
+    import torch.distributed as dist
+    from moldiff_b200.placeholder import make_data_placeholder
+    from moldiff_b200.sharding import gather_predictions, shard_range
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_graphs, rank, world)
+    np.random.seed(2023 + rank)
+    ph = make_data_placeholder(hi - lo)
+    g = torch.Generator().manual_seed(rank)
+    N, Eh = len(ph["batch_node"]), len(ph["batch_halfedge"])
+    pred = [torch.randn(N, 8, generator=g), torch.randn(N, 3, generator=g), torch.randn(Eh, 6, generator=g)]
+    out = gather_predictions(pred, ph["batch_node"], ph["batch_halfedge"], dist, dst=0)
+    if rank == 0:
+        q.put((out["n_graphs"], out["pred"][0].shape[0], out["pred"][2].shape[0], int(out["batch_node"].max()),
+               float(out["pred"][1].sum())))
+    else:
+        q.put((N, Eh, float(pred[1].sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharding_and_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    from moldiff_b200.sharding import shard_sizes
+    assert shard_sizes(7, 2) == [4, 3] and sum(shard_sizes(2048, 8)) == 2048
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 7, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    root = [r for r in res if len(r) == 5][0]
+    other = [r for r in res if len(r) == 3][0]
+    assert root[0] == 7 and root[3] == 6                     # 7 molecules, ids renumbered 0..6
+    assert root[1] > other[0] and root[2] > other[1]         # rank 0's + rank 1's atoms / half-edges
