@@ -31,6 +31,7 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 28); ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
   uint8_t* x_lo = x_hi + tc::ROWS * D * 2;
   uint8_t* stages = x_lo + tc::ROWS * D * 2;              // 2 x 32 KB
   tc::PipeSmem* ps = reinterpret_cast<tc::PipeSmem*>(stages + tc::NSTAGE * tc::STAGE_SLOT);
-  float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 64);     // [2][128]
+  float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 128);     // [2][128]
   int* ls = reinterpret_cast<int*>(stat + 2 * tc::ROWS);
   float* out_tile = reinterpret_cast<float*>(smem_raw);   // [128][OUT_LD] fp32, aliases the E and X planes at the end
 
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
 }
 
 constexpr size_t SMEM_TC_NB = 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2 + tc::NSTAGE * tc::STAGE_SLOT
-                              + 64 + 2 * tc::ROWS * sizeof(float2) + tc::ROWS * sizeof(int) + 64;
-static_assert(sizeof(tc::PipeSmem) <= 64, "PipeSmem must fit its 64-byte slot");
+                              + 128 + 2 * tc::ROWS * sizeof(float2) + tc::ROWS * sizeof(int) + 64;
+static_assert(sizeof(tc::PipeSmem) <= 128, "PipeSmem must fit its 128-byte slot");
 static_assert(SMEM_TC_NB <= 232448, "tc_nodeblock_fwd_kernel exceeds the 227 KB shared-memory limit");
 static_assert((size_t)tc::ROWS * OUT_LD * 4 <= 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2,
               "out tile must fit in the operand planes it aliases");
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
   uint8_t* x_lo = x_hi + tc::ROWS * D * 2;
   uint8_t* stages = x_lo + tc::ROWS * D * 2;
   tc::PipeSmem* ps = reinterpret_cast<tc::PipeSmem*>(stages + tc::NSTAGE * tc::STAGE_SLOT);
-  float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 64);
+  float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * tc::ROWS;
@@ -566,5 +566,5 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
 }
 
 constexpr size_t SMEM_TC_NB_BWD = 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2
-                                  + tc::NSTAGE * tc::STAGE_SLOT + 64 + 2 * tc::ROWS * sizeof(float2) + 64;
+                                  + tc::NSTAGE * tc::STAGE_SLOT + 128 + 2 * tc::ROWS * sizeof(float2) + 64;
 static_assert(SMEM_TC_NB_BWD <= 232448, "tc_nodeblock_bwd_kernel exceeds the 227 KB shared-memory limit");

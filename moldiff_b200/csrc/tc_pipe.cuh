@@ -16,8 +16,8 @@ namespace tc {
 
 constexpr int ROWS = 128;              // tile rows = UMMA M
 constexpr int NTHREADS_TC = 192;       // 4 row warps + producer warp + MMA warp
-constexpr int KB = 32;                 // K columns per weight stage
-constexpr int NSTAGE = 2;
+constexpr int KB = 16;                 // K columns per weight stage
+constexpr int NSTAGE = 4;
 constexpr uint32_t STAGE_SLOT = 256 * KB * 2 * 2;   // bytes reserved per stage (N = 256 worst case): 32 KB
 
 struct PipeSmem {                      // lives in shared memory

@@ -47,7 +47,7 @@ tc_selftest_kernel(const float* __restrict__ X, const uint8_t* __restrict__ w_im
 
 template <int K, int N>
 int launch_tc_selftest(const float* X, const void* w_img, float* Y, int twice, cudaStream_t st) {
-  const size_t smem = 2 * (size_t)tc::ROWS * K * 2 + tc::NSTAGE * tc::STAGE_SLOT + sizeof(tc::PipeSmem) + 64;
+  const size_t smem = 2 * (size_t)tc::ROWS * K * 2 + tc::NSTAGE * tc::STAGE_SLOT + sizeof(tc::PipeSmem) + 128;
   CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_selftest_kernel<K, N><<<1, tc::NTHREADS_TC, smem, st>>>(X, reinterpret_cast<const uint8_t*>(w_img), Y, twice);
   ++g_launches;

@@ -249,7 +249,7 @@ def pack_network(sd, *, kind, net_prefix, num_blocks, update_pos, time_dim=0):
 # ---------------------------------------------------------------------------------------------------------
 # tensor-core operand images (tcgen05 path)
 # ---------------------------------------------------------------------------------------------------------
-TC_KB = 32   # K columns per weight stage; must equal tc::KB in csrc/tc_pipe.cuh
+TC_KB = 16   # K columns per weight stage; must equal tc::KB in csrc/tc_pipe.cuh
 
 
 def split_bf16(w):

@@ -185,12 +185,13 @@ def test_packing_roundtrip_and_tc_images(seeded_models):
     img = packing.tc_image(w.t().contiguous())
     hi, lo = packing.split_bf16(w)                                                 # [N][K]
     assert img.numel() == 2 * 256 * 256
-    # element (n, k) of stage s = k // 32 sits at (n%8)*8 + (n//8)*(32//8)*64 + ((k%32)//8)*64 + k%8  (int16 units)
+    # element (n, k) of stage s = k // KB sits at (n%8)*8 + (n//8)*(KB//8)*64 + ((k%KB)//8)*64 + k%8  (int16 units)
+    KB = packing.TC_KB
     n, k = 37, 170
-    s, kk = divmod(k, 32)
-    base = s * 2 * 256 * 32
-    idx = base + (n % 8) * 8 + (n // 8) * 4 * 64 + (kk // 8) * 64 + kk % 8
-    assert img[idx] == hi[n, k].view(torch.int16) and img[idx + 256 * 32] == lo[n, k].view(torch.int16)
+    s, kk = divmod(k, KB)
+    base = s * 2 * 256 * KB
+    idx = base + (n % 8) * 8 + (n // 8) * (KB // 8) * 64 + (kk // 8) * 64 + kk % 8
+    assert img[idx] == hi[n, k].view(torch.int16) and img[idx + 256 * KB] == lo[n, k].view(torch.int16)
     tcb, tco = packing.pack_tc(sd, net_prefix="denoiser", num_blocks=6, update_pos=True, with_backward=False)
     assert all(x % 128 == 0 for row in tco for x in row if x >= 0)
 
