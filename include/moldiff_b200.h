@@ -212,6 +212,10 @@ int mdb_num_kernel_classes(void);
  * split-bf16 stage images of moldiff_b200/packing.py:tc_image; twice != 0 accumulates the product twice. */
 int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int32_t n, int32_t twice, void* stream);
 
+/* Debug: device int64 buffer [n_tiles][32] that tc_nodeblock_fwd_kernel fills with clock64() phase stamps of its row
+ * thread 0 (NULL = off, the default).  tools/tc_phase_times.py prints the per-phase breakdown. */
+void mdb_debug_set_buffer(void* device_i64_buffer);
+
 /* Diagnostics. */
 const char* mdb_last_error(void);
 int mdb_version(void);

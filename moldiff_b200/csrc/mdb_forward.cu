@@ -669,6 +669,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 thread_local char g_err[512] = "";
 int64_t g_launches = 0;
 bool g_profiling = false;
+long long* g_dbg_stamps = nullptr;   // optional device buffer for in-kernel clock64 phase stamps (mdb_debug_set_buffer)
 struct ProfRec { int cls; cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof;
 
@@ -848,6 +849,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tb;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
+      ta.dbg = g_dbg_stamps;
       LAUNCH(MDB_K_tc_nodeblock, st,
              (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
     }
@@ -950,6 +952,8 @@ int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int3
   if (k == 64 && n == 32) return launch_tc_selftest<64, 32>(x, w_img, y, twice, st);
   return fail(MDB_EINVAL, "mdb_tc_selftest: unsupported (k, n)%s");
 }
+
+void mdb_debug_set_buffer(void* device_i64_buffer) { g_dbg_stamps = reinterpret_cast<long long*>(device_i64_buffer); }
 
 void mdb_profile_begin(void) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

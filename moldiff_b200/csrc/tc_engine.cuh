@@ -180,18 +180,28 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // ---- split-bf16 helpers -----------------------------------------------------------------------------------
 // 8 consecutive k values of one row -> one 16-byte chunk in the hi plane and one in the lo plane.
+// cvt.rn.bf16x2.f32 (F2FP, full rate) packs two values per instruction; the scalar cvt (F2F) is quarter rate.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));   // first source -> upper half
+  return r;
+}
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+    const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);            // exact: bf16 -> fp32 is a 16-bit shift
+    const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+    l[i] = pack_bf16x2(r0, r1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// sigmoid for the tensor-core path: ex2.approx + rcp.approx (~1e-6 relative), 2 MUFU + 3 FP ops
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  return __frcp_rn(1.f + __expf(-x));
 }
 
 // byte offset of the 16-byte chunk (row r, k-chunk c) in an A plane with K columns (LBO = 128, SBO = K/8*128)

@@ -23,7 +23,9 @@ struct TcNbArgs {
   const int *left, *right;
   int n_nodes, n_edges;
   const float* ebuf;          // [E][64] e = edge_embs(cat(h_edge, rbf)) (written by edge_kernel_b)
+  long long* dbg;             // optional [grid][32] clock64 stamps of row thread 0 (phase timing, tools/tc_phase_times.py)
 };
+#define TC_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
 
 constexpr int OUT_LD = 260;   // fp32 row stride of the out tile in smem: 1040 B = 16 (mod 128) -> conflict-free rows
 constexpr int TC_NRW = 8;     // row warps: thread (w, t) owns row 32 * (w % 4) + t, columns [128 * (w / 4), +128)
@@ -67,13 +69,17 @@ __device__ __forceinline__ void add_row128(float (&v)[128], const float* __restr
 // 128 values two-pass, the halves are merged exactly (Chan et al.) through `stat`, then v <- relu(LN(v) * g + b).
 __device__ __forceinline__ void ln_relu_half(float (&v)[128], const float* __restrict__ gamma,
                                              const float* __restrict__ beta, float2* stat, int row, int half) {
-  float s = 0.f;
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};                    // 4 independent chains: 32-deep instead of 128-deep
 #pragma unroll
-  for (int i = 0; i < 128; ++i) s += v[i];
-  const float m_h = s * (1.f / 128.f);
-  float q = 0.f;
+  for (int i = 0; i < 128; i += 4) { s4[0] += v[i]; s4[1] += v[i + 1]; s4[2] += v[i + 2]; s4[3] += v[i + 3]; }
+  const float m_h = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 128.f);
+  float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 128; ++i) { const float d = v[i] - m_h; q = fmaf(d, d, q); }
+  for (int i = 0; i < 128; i += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const float d = v[i + u] - m_h; q4[u] = fmaf(d, d, q4[u]); }
+  }
+  const float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
   stat[half * tc::ROWS + row] = make_float2(m_h, q);
   asm volatile("bar.sync 1, 256;" ::: "memory");
   const float2 o = stat[(half ^ 1) * tc::ROWS + row];
@@ -123,6 +129,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
   const float* blob = a.blob;
   const BlkOff& off = a.off;
   const Tables& tb = a.tb;
+  TC_STAMP(0);
   tc::Pipe p;
   tc::pipe_init<TC_NRW>(p, ps, stages);
   if (warp == TC_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
@@ -141,6 +148,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
   const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t D0 = 0, D1 = 256;          // TMEM column bases: msg accumulator / everything else
   const int rr = my_r < 0 ? 0 : my_r;
+  TC_STAMP(1);
 
   // ---- rows: e tile -> E planes (each thread 32 of the 64 columns of its row)
   if (p.role == 0) {
@@ -155,17 +163,20 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     }
     tc::store_a32<C>(e_hi, e_lo, row, k0, v);
     tc::rows_publish(p);
+    TC_STAMP(6);
   }
   // G1: edge_net.net.0                                                            graph.py:42
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), D1, false, true, true);
   if (p.role == 0) {
     tc::rows_wait_acc(p);
+    TC_STAMP(2);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
     add_vec128(v, W_(NB_EN1_B) + hc);
     ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
+    TC_STAMP(7);
   }
   // G2: edge_net.net.3 ; m = he * node_net(x)[col]                               graph.py:43
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_EN2), D1, false, true, true);
@@ -174,6 +185,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
 #pragma unroll
     for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(hn + i));
     tc::rows_wait_acc(p);
+    TC_STAMP(3);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
     add_vec128(v, W_(NB_EN2_B) + hc);
@@ -184,6 +196,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     }
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
+    TC_STAMP(8);
   }
   // G3: msg_net -> D0 (stays in TMEM) ; G4: gate.net.0 edge columns -> D1         graph.py:43,46
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_MSG), D0, false, true, false);
@@ -193,17 +206,20 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
 #pragma unroll
     for (int i = 0; i < 128; i += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(gxr + i));
     tc::rows_wait_acc(p);
+    TC_STAMP(4);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
     add_row128(v, gxr);                                    // hoisted node / time / bias part of gate.net.0
     ln_relu_half(v, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
+    TC_STAMP(9);
   }
   // G5: gate.net.3                                                                graph.py:46
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_G2), D1, false, true, true);
   if (p.role == 0) {
     tc::rows_wait_acc(p);
+    TC_STAMP(5);
     // out = (msg + b) * sigmoid(gate + b)  -> smem tile (all operand planes are dead now)     graph.py:47
     {
       float v[128];
@@ -212,8 +228,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
 #pragma unroll
       for (int i = 0; i < 128; i += 4)                    // park sigmoid(gate) in the tile, then fold msg in
         *reinterpret_cast<float4*>(out_tile + row * OUT_LD + hc + i) =
-            make_float4(1.f / (1.f + expf(-v[i])), 1.f / (1.f + expf(-v[i + 1])), 1.f / (1.f + expf(-v[i + 2])),
-                        1.f / (1.f + expf(-v[i + 3])));
+            make_float4(tc::fast_sigmoid(v[i]), tc::fast_sigmoid(v[i + 1]), tc::fast_sigmoid(v[i + 2]),
+                        tc::fast_sigmoid(v[i + 3]));
       load_half_row(lane_base + D0 + hc, v);
       add_vec128(v, W_(NB_MSG_B) + hc);
 #pragma unroll
@@ -238,6 +254,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     }
     if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + tid, s0);
   }
+  TC_STAMP(15);
   __syncthreads();
   if (warp == TC_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
 }
@@ -446,7 +463,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
     load_half_row(lane_base + D1 + hc, sg);
     add_vec128(sg, W_(NB_G2_B) + hc);
 #pragma unroll
-    for (int i = 0; i < 128; ++i) sg[i] = 1.f / (1.f + expf(-sg[i]));
+    for (int i = 0; i < 128; ++i) sg[i] = tc::fast_sigmoid(sg[i]);
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
       float m[32];
