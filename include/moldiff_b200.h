@@ -129,6 +129,8 @@ typedef struct mdb_net_desc {
   int32_t kind;                 /* 0 = bare NodeEdgeNet, 1 = MolDiff, 2 = BondPredictor           */
   int64_t head_off[MDB_NUM_HEAD_SLOTS];                        /* float offsets into blob, -1 = absent */
   int64_t block_off[MDB_MAX_BLOCKS][MDB_NUM_BLOCK_SLOTS];
+  const float* blob_host;       /* host copy of `blob` (bias / LayerNorm vectors are passed to the tensor-core   */
+                                /* kernels by value, i.e. through the constant bank); required when tc_blob set  */
   const void* tc_blob;          /* device: tensor-core operand images, or NULL = fp32 FFMA path only    */
   int64_t tc_block_off[MDB_MAX_BLOCKS][MDB_NUM_TC_SLOTS];      /* byte offsets into tc_blob, -1 = absent */
 } mdb_net_desc;

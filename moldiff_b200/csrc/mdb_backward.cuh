@@ -741,13 +741,14 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     fill_blk(ea.off, net, i);
     ea.e = sv.e + (size_t)i * EC; ea.sl = sv.slsr + (size_t)i * 2 * NC; ea.fl = tb.fl; ea.fr = tb.fr;
     LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
-    if (net->tc_blob != nullptr && net->tc_block_off[i][MDB_T_BT_NB_G2] >= 0) {
+    if (net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_NB_G2] >= 0) {
       TcNbBwdArgs ta;
       memset(&ta, 0, sizeof(ta));
       ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tb;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
       ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de;
+      fill_nb_vecs(ta.v, net->blob_host, ea.off);
       LAUNCH(MDB_K_tc_nodeblock_bwd, st,
              (tc_nodeblock_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB_BWD, st>>>(ta)));
     } else {

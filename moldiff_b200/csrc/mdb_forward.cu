@@ -840,7 +840,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     fill_blk(ea.off, net, i);
     ea.sl = sl_of(i); ea.fl = fl_of(i); ea.fr = fr_of(i); ea.ebuf = in.save ? sv.e + (size_t)i * EC : tb.ebuf;
     ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
-    const bool tc_nb = net->tc_blob != nullptr && net->tc_block_off[i][MDB_T_NB_EN1] >= 0;
+    const bool tc_nb = net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_NB_EN1] >= 0;
     ea.skip_nodeblock = tc_nb ? 1 : 0;
     if (E > 0) LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
     if (E > 0 && tc_nb) {
@@ -850,6 +850,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
       ta.dbg = g_dbg_stamps;
+      fill_nb_vecs(ta.v, net->blob_host, ea.off);
       LAUNCH(MDB_K_tc_nodeblock, st,
              (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
     }

@@ -14,6 +14,12 @@
 struct TcOff { int64_t o[MDB_NUM_TC_SLOTS]; };   // byte offsets into the tc blob
 #define TCW_(slot) (a.tc_blob + a.tco.o[MDB_T_##slot])
 
+// Per-column parameter vectors of the NodeBlock edge path, passed BY VALUE: they then live in the constant bank
+// and every row thread reads them with warp-uniform constant loads instead of 96 LDG per LayerNorm epilogue.
+struct NbVecs {
+  float en1_b[D], en1_g[D], en1_be[D], en2_b[D], msg_b[D], g1_g[D], g1_be[D], g2_b[D];
+};
+
 struct TcNbArgs {
   const float* blob;          // fp32 blob: biases / LayerNorm parameters
   const uint8_t* tc_blob;     // split-bf16 weight stage images
@@ -23,6 +29,7 @@ struct TcNbArgs {
   const int *left, *right;
   int n_nodes, n_edges;
   const float* ebuf;          // [E][64] e = edge_embs(cat(h_edge, rbf)) (written by edge_kernel_b)
+  NbVecs v;
   long long* dbg;             // optional [grid][32] clock64 stamps of row thread 0 (phase timing, tools/tc_phase_times.py)
 };
 #define TC_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
@@ -48,13 +55,10 @@ __device__ __forceinline__ void load_half_row(uint32_t taddr, float (&v)[128]) {
   }
 }
 
-// v += vec[0:128]  (vec: global, identical for every thread of the warp -> broadcast loads)
+// v += vec[0:128]  (vec: kernel-argument array in the constant bank, warp-uniform address)
 __device__ __forceinline__ void add_vec128(float (&v)[128], const float* __restrict__ vec) {
 #pragma unroll
-  for (int i = 0; i < 128; i += 4) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(vec + i));
-    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-  }
+  for (int i = 0; i < 128; ++i) v[i] += vec[i];
 }
 // v += row[0:128]  (row: this thread's own gathered table row)
 __device__ __forceinline__ void add_row128(float (&v)[128], const float* __restrict__ row) {
@@ -87,14 +91,7 @@ __device__ __forceinline__ void ln_relu_half(float (&v)[128], const float* __res
   const float dm = m_h - o.x;
   const float rstd = 1.f / sqrtf((q + o.y + dm * dm * 64.f) * (1.f / 256.f) + LN_EPS);
 #pragma unroll
-  for (int i = 0; i < 128; i += 4) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
-    v[i] = fmaxf((v[i] - mean) * rstd * g.x + b.x, 0.f);
-    v[i + 1] = fmaxf((v[i + 1] - mean) * rstd * g.y + b.y, 0.f);
-    v[i + 2] = fmaxf((v[i + 2] - mean) * rstd * g.z + b.z, 0.f);
-    v[i + 3] = fmaxf((v[i + 3] - mean) * rstd * g.w + b.w, 0.f);
-  }
+  for (int i = 0; i < 128; ++i) v[i] = fmaxf((v[i] - mean) * rstd * gamma[i] + beta[i], 0.f);
 }
 
 // this thread's 128 values -> columns [k0, k0 + 128) of row r of the K = 256 A planes
@@ -112,7 +109,7 @@ __device__ __forceinline__ void store_half_row_a(uint8_t* a_hi, uint8_t* a_lo, i
   }
 }
 
-__global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(const TcNbArgs a) {
+__global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(const __grid_constant__ TcNbArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* e_hi = smem_raw;                               // 128 x 64 bf16 = 16 KB
   uint8_t* e_lo = e_hi + tc::ROWS * C * 2;
@@ -126,8 +123,6 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * tc::ROWS;
-  const float* blob = a.blob;
-  const BlkOff& off = a.off;
   const Tables& tb = a.tb;
   TC_STAMP(0);
   tc::Pipe p;
@@ -172,8 +167,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     TC_STAMP(2);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
-    add_vec128(v, W_(NB_EN1_B) + hc);
-    ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
+    add_vec128(v, a.v.en1_b + hc);
+    ln_relu_half(v, a.v.en1_g + hc, a.v.en1_be + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
     TC_STAMP(7);
@@ -188,7 +183,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     TC_STAMP(3);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
-    add_vec128(v, W_(NB_EN2_B) + hc);
+    add_vec128(v, a.v.en2_b + hc);
 #pragma unroll
     for (int i = 0; i < 128; i += 4) {
       const float4 t4 = *reinterpret_cast<const float4*>(hn + i);
@@ -210,7 +205,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
     add_row128(v, gxr);                                    // hoisted node / time / bias part of gate.net.0
-    ln_relu_half(v, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, stat, row, half);
+    ln_relu_half(v, a.v.g1_g + hc, a.v.g1_be + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
     TC_STAMP(9);
@@ -224,14 +219,14 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     {
       float v[128];
       load_half_row(lane_base + D1 + hc, v);
-      add_vec128(v, W_(NB_G2_B) + hc);
+      add_vec128(v, a.v.g2_b + hc);
 #pragma unroll
       for (int i = 0; i < 128; i += 4)                    // park sigmoid(gate) in the tile, then fold msg in
         *reinterpret_cast<float4*>(out_tile + row * OUT_LD + hc + i) =
             make_float4(tc::fast_sigmoid(v[i]), tc::fast_sigmoid(v[i + 1]), tc::fast_sigmoid(v[i + 2]),
                         tc::fast_sigmoid(v[i + 3]));
       load_half_row(lane_base + D0 + hc, v);
-      add_vec128(v, W_(NB_MSG_B) + hc);
+      add_vec128(v, a.v.msg_b + hc);
 #pragma unroll
       for (int i = 0; i < 128; i += 4) {
         float4* o = reinterpret_cast<float4*>(out_tile + row * OUT_LD + hc + i);
@@ -259,6 +254,13 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
   if (warp == TC_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
 }
 
+// host: copy the eight 256-float parameter vectors of block `off` out of the host blob
+inline void fill_nb_vecs(NbVecs& v, const float* blob_host, const BlkOff& off) {
+  auto cp = [&](float* dst, int slot) { memcpy(dst, blob_host + off.o[slot], D * sizeof(float)); };
+  cp(v.en1_b, MDB_S_NB_EN1_B); cp(v.en1_g, MDB_S_NB_EN1_G); cp(v.en1_be, MDB_S_NB_EN1_BE); cp(v.en2_b, MDB_S_NB_EN2_B);
+  cp(v.msg_b, MDB_S_NB_MSG_B); cp(v.g1_g, MDB_S_NB_G1_G); cp(v.g1_be, MDB_S_NB_G1_BE); cp(v.g2_b, MDB_S_NB_G2_B);
+}
+
 constexpr size_t SMEM_TC_NB = 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2 + tc::NSTAGE * tc::STAGE_SLOT
                               + 128 + 2 * tc::ROWS * sizeof(float2) + tc::ROWS * sizeof(int) + 64;
 static_assert(sizeof(tc::PipeSmem) <= 128, "PipeSmem must fit its 128-byte slot");
@@ -281,6 +283,7 @@ struct TcNbBwdArgs {
   const float* dagg;     // [N][256] d/d (aggregated messages)
   float *dgx, *dhn;      // [N][256] scatter targets (pre-zeroed)
   float* de;             // [E][64]  d/d e, accumulated (+=)
+  NbVecs v;
 };
 
 // cross-half exchange of two partial values per row; returns the partner's pair
@@ -303,10 +306,7 @@ __device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restr
     tc::tmem_ld32(taddr + c0, a);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      if (HAS_BIAS) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-        a[i] += b.x; a[i + 1] += b.y; a[i + 2] += b.z; a[i + 3] += b.w;
-      }
+      if (HAS_BIAS) { a[i] += bias[c0 + i]; a[i + 1] += bias[c0 + i + 1]; a[i + 2] += bias[c0 + i + 2]; a[i + 3] += bias[c0 + i + 3]; }
       if (HAS_EXTRA) {
         const float4 x = *reinterpret_cast<const float4*>(extra + c0 + i);
         a[i] += x.x; a[i + 1] += x.y; a[i + 2] += x.z; a[i + 3] += x.w;
@@ -339,9 +339,8 @@ __device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restr
     pre(cc * 32, a);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + cc * 32 + i));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + cc * 32 + i));
-      const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+      const float gg[4] = {gamma[cc * 32 + i], gamma[cc * 32 + i + 1], gamma[cc * 32 + i + 2], gamma[cc * 32 + i + 3]};
+      const float bb[4] = {beta[cc * 32 + i], beta[cc * 32 + i + 1], beta[cc * 32 + i + 2], beta[cc * 32 + i + 3]};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float xh = (a[i + u] - mean) * rstd;
@@ -366,7 +365,7 @@ __device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(const TcNbBwdArgs a) {
+__global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(const __grid_constant__ TcNbBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* e_hi = smem_raw;
   uint8_t* e_lo = e_hi + tc::ROWS * C * 2;
@@ -378,8 +377,6 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * tc::ROWS;
-  const float* blob = a.blob;
-  const BlkOff& off = a.off;
   const Tables& tb = a.tb;
   tc::Pipe p;
   tc::pipe_init<TC_NRW>(p, ps, stages);
@@ -418,8 +415,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
     tc::rows_wait_acc(p);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
-    add_vec128(v, W_(NB_EN1_B) + hc);
-    ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
+    add_vec128(v, a.v.en1_b + hc);
+    ln_relu_half(v, a.v.en1_g + hc, a.v.en1_be + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
   }
@@ -430,7 +427,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
     tc::rows_wait_acc(p);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
-    add_vec128(v, W_(NB_EN2_B) + hc);
+    add_vec128(v, a.v.en2_b + hc);
 #pragma unroll
     for (int i = 0; i < 128; i += 4) {
       const float4 t4 = *reinterpret_cast<const float4*>(hn + i);
@@ -448,7 +445,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
     add_row128(v, gxr);
-    ln_relu_half(v, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, stat, row, half);
+    ln_relu_half(v, a.v.g1_g + hc, a.v.g1_be + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
   }
@@ -461,7 +458,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
     tc::rows_wait_acc(p);
     float sg[128];
     load_half_row(lane_base + D1 + hc, sg);
-    add_vec128(sg, W_(NB_G2_B) + hc);
+    add_vec128(sg, a.v.g2_b + hc);
 #pragma unroll
     for (int i = 0; i < 128; ++i) sg[i] = tc::fast_sigmoid(sg[i]);
 #pragma unroll
@@ -470,7 +467,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
       tc::tmem_ld32(lane_base + D0 + hc + cc * 32, m);
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(W_(NB_MSG_B) + hc + cc * 32 + i));
+        const float* bp = a.v.msg_b + hc + cc * 32 + i;
+        const float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
         float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) dz = *reinterpret_cast<const float4*>(dout + cc * 32 + i);
         const float bb[4] = {b.x, b.y, b.z, b.w}, dd[4] = {dz.x, dz.y, dz.z, dz.w};
@@ -499,7 +497,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), D1, false, true, true);
   if (p.role == 0) {
     tc::rows_wait_acc(p);
-    ln_bwd_half<false, true>(lane_base + D1 + hc, nullptr, gxr, W_(NB_G1_G) + hc, W_(NB_G1_BE) + hc, dr, stat, row, half);
+    ln_bwd_half<false, true>(lane_base + D1 + hc, nullptr, gxr, a.v.g1_g + hc, a.v.g1_be + hc, dr, stat, row, half);
     if (valid) {
       float* dst = a.dgx + (size_t)rr * D + hc;
 #pragma unroll
@@ -524,8 +522,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
     tc::rows_wait_acc(p);
     float v[128];
     load_half_row(lane_base + D1 + hc, v);
-    add_vec128(v, W_(NB_EN1_B) + hc);
-    ln_relu_half(v, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc, stat, row, half);
+    add_vec128(v, a.v.en1_b + hc);
+    ln_relu_half(v, a.v.en1_g + hc, a.v.en1_be + hc, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, v);
     tc::rows_publish(p);
   }
@@ -540,7 +538,8 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
       tc::tmem_ld32(lane_base + D0 + hc + cc * 32, dm);
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(W_(NB_EN2_B) + hc + cc * 32 + i));
+        const float* bp = a.v.en2_b + hc + cc * 32 + i;
+        const float4 b = make_float4(bp[0], bp[1], bp[2], bp[3]);
         const float4 h = *reinterpret_cast<const float4*>(hn + cc * 32 + i);
         if (valid)
           tc::red_add_v4(dst + cc * 32 + i, dm[i] * (he[i] + b.x), dm[i + 1] * (he[i + 1] + b.y),
@@ -557,7 +556,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
   if (p.role == 0) {
     tc::rows_wait_acc(p);
     load_half_row(lane_base + D1 + hc, dr);
-    ln_bwd_half<true, false>(lane_base + D0 + hc, W_(NB_EN1_B) + hc, nullptr, W_(NB_EN1_G) + hc, W_(NB_EN1_BE) + hc,
+    ln_bwd_half<true, false>(lane_base + D0 + hc, a.v.en1_b + hc, nullptr, a.v.en1_g + hc, a.v.en1_be + hc,
                              dr, stat, row, half);
     store_half_row_a(x_hi, x_lo, row, hc, dr);
     tc::rows_publish(p);

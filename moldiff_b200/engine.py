@@ -38,6 +38,7 @@ class NetDesc(C.Structure):
         ("kind", C.c_int32),
         ("head_off", C.c_int64 * NUM_HEAD),
         ("block_off", (C.c_int64 * NUM_BLOCK) * MAX_BLOCKS),
+        ("blob_host", C.c_void_p),
         ("tc_blob", C.c_void_p),
         ("tc_block_off", (C.c_int64 * NUM_TC) * MAX_BLOCKS),
     ]
@@ -174,8 +175,10 @@ class PackedNet:
         if self.device.type != "cuda":
             raise MoldiffB200Error("PackedNet needs a CUDA device: moldiff_b200 has no CPU path")
         self.blob = blob.to(self.device)
+        self.blob_cpu = blob.contiguous()          # host copy: small parameter vectors travel as kernel arguments
         d = NetDesc()
         d.blob = self.blob.data_ptr()
+        d.blob_host = self.blob_cpu.data_ptr()
         d.num_blocks = num_blocks
         d.update_pos = int(bool(update_pos))
         d.rbf_start = float(start)
