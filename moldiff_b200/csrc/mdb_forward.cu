@@ -662,6 +662,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 }
 
 #include "tc_nodeblock.cuh"
+#include "tc_bondffn.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -762,6 +763,7 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(edge_kernel_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_EDGE_D));
   CUDA_TRY(cudaFuncSetAttribute(edge_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DEC));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
   done = true;
   return MDB_OK;
 }
@@ -842,7 +844,18 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
     const bool tc_nb = net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_NB_EN1] >= 0;
     ea.skip_nodeblock = tc_nb ? 1 : 0;
-    if (E > 0) LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
+    const bool tc_ffn = tc_nb && net->tc_block_off[i][MDB_T_EE] >= 0;
+    if (E > 0 && tc_ffn) {
+      TcFfnArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tb;
+      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) fa.tco.o[s] = net->tc_block_off[i][s];
+      fa.left = plan->left; fa.right = plan->right; fa.n_nodes = N; fa.n_edges = E;
+      fa.pos = pos_cur; fa.rbf_lo = net->rbf_start; fa.rbf_hi = net->rbf_stop; fa.ebuf = ea.ebuf; fa.sl = ea.sl;
+      fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
+      LAUNCH(MDB_K_tc_bondffn, st,
+             (tc_bondffn_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
+    } else
     if (E > 0 && tc_nb) {
       TcNbArgs ta;
       memset(&ta, 0, sizeof(ta));
@@ -951,6 +964,10 @@ int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int3
   if (k == 256 && n == 64) return launch_tc_selftest<256, 64>(x, w_img, y, twice, st);
   if (k == 128 && n == 128) return launch_tc_selftest<128, 128>(x, w_img, y, twice, st);
   if (k == 64 && n == 32) return launch_tc_selftest<64, 32>(x, w_img, y, twice, st);
+  if (k == 80 && n == 64) return launch_tc_selftest<80, 64>(x, w_img, y, twice, st);
+  if (k == 64 && n == 128) return launch_tc_selftest<64, 128>(x, w_img, y, twice, st);
+  if (k == 32 && n == 64) return launch_tc_selftest<32, 64>(x, w_img, y, twice, st);
+  if (k == 128 && n == 64) return launch_tc_selftest<128, 64>(x, w_img, y, twice, st);
   return fail(MDB_EINVAL, "mdb_tc_selftest: unsupported (k, n)%s");
 }
 

@@ -155,6 +155,25 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
+// 16-column variant (narrow accumulators: N = 32 split between two threads)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // registers -> TMEM: 32 consecutive fp32 columns of this thread's lane (used to park fp32 tiles between GEMMs)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
@@ -215,6 +234,22 @@ template <int K>
 __device__ __forceinline__ void store_a32(uint8_t* a_hi, uint8_t* a_lo, int r, int k0, const float (&v)[32]) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = v[c * 8 + i];
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const uint32_t off = a_chunk_off<K>(r, k0 / 8 + c);
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  }
+}
+
+// Store NC (multiple of 8) consecutive fp32 values of row r, starting at column k0, into A planes with K columns.
+template <int K, int NC>
+__device__ __forceinline__ void store_a(uint8_t* a_hi, uint8_t* a_lo, int r, int k0, const float (&v)[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC / 8; ++c) {
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = v[c * 8 + i];

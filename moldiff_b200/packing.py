@@ -291,6 +291,16 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
         "NB_GE": _t(g0[:, :EDGE_DIM]),                         # [64][256]
         "NB_G2": _t(sd[nb + ".gate.net.3.weight"]),
     }
+    o["EE"] = _t(sd[f"{net_prefix}.edge_embs.{i}.weight"])     # [80][64]
+    eb = f"{net_prefix}.edge_blocks.{i}"
+    for tag, sub in (("EL", "bond_ffn_left"), ("ER", "bond_ffn_right")):
+        p = f"{eb}.{sub}"
+        gw = sd[p + ".gate.net.0.weight"]
+        o[f"{tag}_BL"] = _t(sd[p + ".bond_linear.weight"])                 # [64][128]
+        o[f"{tag}_GB"] = _t(gw[:, :EDGE_DIM])                              # [64][32]
+        o[f"{tag}_I1"] = _t(sd[p + ".inter_module.net.0.weight"])          # [128][128]
+        o[f"{tag}_G2"] = _t(sd[p + ".gate.net.3.weight"])                  # [32][64]
+        o[f"{tag}_I2"] = _t(sd[p + ".inter_module.net.3.weight"])          # [128][64]
     if with_backward:                                          # dX = dY @ W  with W stored [out][in] = [K][N]
         o["BT_NB_G2"] = _asis(sd[nb + ".gate.net.3.weight"])
         o["BT_NB_GE"] = _asis(g0[:, :EDGE_DIM])                # [256][64]

@@ -40,7 +40,7 @@ def test_library_loaded_and_counts_launches(gpu_models, dev):
     before = engine.launch_count()
     cuda_moldiff(gpu_models[0], batch_inputs(B=2), dev)
     tc = gpu_models[0]._packed_net(dev).tc_blob is not None
-    # init x2, pre(0), 3 per block (+1 tensor-core NodeBlock kernel per block), edge decode
+    # init x2, pre(0), per block: edge kernel B (fp32) or its two tensor-core kernels, node kernel, edge kernel D; edge decode
     assert engine.launch_count() - before == 2 + 1 + (4 if tc else 3) * 6 + 1
 
 

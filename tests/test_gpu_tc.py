@@ -6,7 +6,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("k,n", [(64, 256), (256, 256), (256, 64), (128, 128), (64, 32)])
+@pytest.mark.parametrize("k,n", [(64, 256), (256, 256), (256, 64), (128, 128), (64, 32), (80, 64), (64, 128), (32, 64), (128, 64)])
 @pytest.mark.parametrize("twice", [False, True])
 def test_tc_gemm_matches_fp64(k, n, twice):
     from moldiff_b200 import engine
