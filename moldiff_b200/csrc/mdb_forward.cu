@@ -855,7 +855,9 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
       LAUNCH(MDB_K_tc_bondffn, st,
              (tc_bondffn_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
-    } else
+    } else if (E > 0) {
+      LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
+    }
     if (E > 0 && tc_nb) {
       TcNbArgs ta;
       memset(&ta, 0, sizeof(ta));

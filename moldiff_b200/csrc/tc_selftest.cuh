@@ -20,11 +20,11 @@ tc_selftest_kernel(const float* __restrict__ X, const uint8_t* __restrict__ w_im
   __syncthreads();
   tc::fence_after_sync();
   if (p.role == 0) {
-    for (int k0 = 0; k0 < K; k0 += 32) {
-      float v[32];
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      float v[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = X[(size_t)tid * K + k0 + i];
-      tc::store_a32<K>(a_hi, a_lo, tid, k0, v);
+      for (int i = 0; i < 16; ++i) v[i] = X[(size_t)tid * K + k0 + i];
+      tc::store_a<K, 16>(a_hi, a_lo, tid, k0, v);
     }
     tc::rows_publish(p);
   }
