@@ -110,7 +110,10 @@ enum mdb_head_slot {
   X(PU_PB) X(PU_PN) X(PU_I1)                                /* PosUpdate edge_lin big Linears        */ \
   X(EE)                                                     /* edge_embs (80 -> 64)                  */ \
   X(EL_BL) X(EL_GB) X(EL_I1) X(EL_G2) X(EL_I2)              /* bond_ffn_left per-edge Linears        */ \
-  X(ER_BL) X(ER_GB) X(ER_I1) X(ER_G2) X(ER_I2)              /* bond_ffn_right                        */
+  X(ER_BL) X(ER_GB) X(ER_I1) X(ER_G2) X(ER_I2)              /* bond_ffn_right                        */ \
+  X(BT_EEH) X(BT_EEG)                                       /* edge_embs, transposed use (backward)  */ \
+  X(BT_EL_G2) X(BT_EL_I2) X(BT_EL_GB) X(BT_EL_I1) X(BT_EL_BL) /* bond_ffn_left, transposed use       */ \
+  X(BT_ER_G2) X(BT_ER_I2) X(BT_ER_GB) X(BT_ER_I1) X(BT_ER_BL)
 
 enum mdb_tc_slot {
 #define MDB_X(name) MDB_T_##name,

@@ -682,6 +682,7 @@ int ensure_bwd_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(bwd_edge_nodeblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_NB));
   CUDA_TRY(cudaFuncSetAttribute(bwd_edge_bondffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_FFN));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD));
   done = true;
   return MDB_OK;
 }
@@ -754,7 +755,20 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     } else {
       LAUNCH(MDB_K_bwd_edge_nodeblock, st, (bwd_edge_nodeblock_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_NB, st>>>(ea)));
     }
-    LAUNCH(MDB_K_bwd_edge_bondffn, st, (bwd_edge_bondffn_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_FFN, st>>>(ea)));
+    if (net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_EEH] >= 0) {
+      TcFfnBwdArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tb;
+      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) fa.tco.o[s] = net->tc_block_off[i][s];
+      fa.left = plan->left; fa.right = plan->right; fa.n_nodes = N; fa.n_edges = E;
+      fa.e = ea.e; fa.dul = sv.dul; fa.dur = sv.dur; fa.dnl = sv.dnl; fa.dgn = sv.dgn;
+      fa.de_in = sv.de; fa.dh = sv.dh; fa.dg = sv.dg;
+      fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
+      LAUNCH(MDB_K_tc_bondffn_bwd, st,
+             (tc_bondffn_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN_BWD, st>>>(fa)));
+    } else {
+      LAUNCH(MDB_K_bwd_edge_bondffn, st, (bwd_edge_bondffn_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_FFN, st>>>(ea)));
+    }
   }
   LAUNCH(MDB_K_bwd_pos, st,
          (bwd_pos_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, plan->left, plan->right, pos, sv.dg,

@@ -307,6 +307,17 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
         o["BT_NB_MSG"] = _asis(sd[nb + ".msg_net.weight"])
         o["BT_NB_EN2"] = _asis(sd[nb + ".edge_net.net.3.weight"])
         o["BT_NB_EN1"] = _asis(sd[nb + ".edge_net.net.0.weight"])   # [256][64]
+        ee = sd[f"{net_prefix}.edge_embs.{i}.weight"]               # [64][80]
+        o["BT_EEH"] = _asis(ee[:, :EDGE_DIM])                       # [64][64]
+        o["BT_EEG"] = _pad_cols(_asis(ee[:, EDGE_DIM:]), 32)        # [64][16 -> 32]
+        for tag, sub in (("EL", "bond_ffn_left"), ("ER", "bond_ffn_right")):
+            p = f"{eb}.{sub}"
+            gw = sd[p + ".gate.net.0.weight"]
+            o[f"BT_{tag}_G2"] = _asis(sd[p + ".gate.net.3.weight"])            # [64][32]
+            o[f"BT_{tag}_I2"] = _asis(sd[p + ".inter_module.net.3.weight"])    # [64][128]
+            o[f"BT_{tag}_GB"] = _asis(gw[:, :EDGE_DIM])                        # [32][64]
+            o[f"BT_{tag}_I1"] = _asis(sd[p + ".inter_module.net.0.weight"])    # [128][128]
+            o[f"BT_{tag}_BL"] = _asis(sd[p + ".bond_linear.weight"])           # [128][64]
     if update_pos:
         pb = f"{net_prefix}.pos_blocks.{i}.edge_lin"
         o["PU_PB"] = _t(sd[pb + ".bond_linear.weight"])        # [64][256]
