@@ -271,7 +271,7 @@ def tc_image(w_kn):
     k, n = w_kn.shape
     if k % TC_KB or n % 16:
         raise ValueError(f"tc_image: K={k} must be a multiple of {TC_KB} and N={n} of 16")
-    hi, lo = split_bf16(w_kn.detach().to(torch.float32).t().contiguous())   # [N][K]
+    hi, lo = split_bf16(w_kn.detach().to(torch.float32).cpu().t().contiguous())   # [N][K]
     parts = []
     for s in range(k // TC_KB):
         sl = slice(s * TC_KB, (s + 1) * TC_KB)
