@@ -274,7 +274,8 @@ def main():
         achieved = flop / (avg_ms * 1e-3) / 1e12
         roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
-                "avg_launch_ms": avg_ms, "note": "logical as-written GEMM FLOPs of the fused layer; fp32 FFMA path",
+                "avg_launch_ms": avg_ms, "note": "achieved = reference-as-written GEMM FLOPs of the layer part this kernel computes / CUDA-event time; "
+                        "tc_* kernels execute them as 3 split-bf16 tcgen05 MMAs after per-node hoisting, others as fp32 FFMA",
                 "hbm_algorithmic_gbs": (512.0 * E + 2080.0 * N) / (avg_ms * 1e-3) / 1e9,
                 "share_of_step": info["ms_total"] / max(sum(v["ms_total"] for v in prof.values()), 1e-9),
                 "per_kernel_ms": {k: round(v["ms_total"] / 3, 4) for k, v in prof.items()}}

@@ -107,7 +107,8 @@ enum mdb_head_slot {
 #define MDB_TC_SLOTS(X)                                                                            \
   X(NB_EN1) X(NB_EN2) X(NB_MSG) X(NB_GE) X(NB_G2)          /* NodeBlock per-edge Linears, forward   */ \
   X(BT_NB_G2) X(BT_NB_GE) X(BT_NB_MSG) X(BT_NB_EN2) X(BT_NB_EN1) /* same, transposed use (backward) */ \
-  X(PU_PB) X(PU_PN) X(PU_I1)                                /* PosUpdate edge_lin big Linears        */ \
+  X(PU_PB) X(PU_PN) X(PU_I1) X(PU_GB) X(PU_GN)              /* PosUpdate edge_lin Linears            */ \
+  X(EB_SELF) X(EB_OUT)                                      /* EdgeBlock tail Linears (64 -> 64)     */ \
   X(EE)                                                     /* edge_embs (80 -> 64)                  */ \
   X(EL_BL) X(EL_GB) X(EL_I1) X(EL_G2) X(EL_I2)              /* bond_ffn_left per-edge Linears        */ \
   X(ER_BL) X(ER_GB) X(ER_I1) X(ER_G2) X(ER_I2)              /* bond_ffn_right                        */ \
@@ -199,7 +200,7 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
   X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
-  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_posupdate) X(tc_bondffn) X(tc_bondffn_bwd)
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,

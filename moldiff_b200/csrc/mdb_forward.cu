@@ -663,6 +663,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 
 #include "tc_nodeblock.cuh"
 #include "tc_bondffn.cuh"
+#include "tc_edge_d.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -764,6 +765,7 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(edge_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DEC));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
+  CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
   done = true;
   return MDB_OK;
 }
@@ -877,7 +879,19 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     na.agg_save = in.save ? sv.agg + (size_t)i * ND : nullptr;
     na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
     LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
-    if (E > 0) LAUNCH(MDB_K_edge_d, st, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea)));
+    if (E > 0 && tc_nb && net->tc_block_off[i][MDB_T_EB_SELF] >= 0) {
+      TcEdgeDArgs da;
+      memset(&da, 0, sizeof(da));
+      da.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); da.tb = tb;
+      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) da.tco.o[s] = net->tc_block_off[i][s];
+      da.left = plan->left; da.right = plan->right; da.n_nodes = N; da.n_edges = E; da.update_pos = net->update_pos;
+      da.ebuf = ea.ebuf; da.sl = ea.sl; da.fl = ea.fl; da.fr = ea.fr; da.pos_cur = pos_cur; da.pos_nxt = pos_nxt;
+      fill_edge_d_vecs(da.v, net->blob_host, ea.off, net->update_pos != 0);
+      LAUNCH(MDB_K_tc_edge_d, st,
+             (tc_edge_d_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, st>>>(da)));
+    } else if (E > 0) {
+      LAUNCH(MDB_K_edge_d, st, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea)));
+    }
     if (net->update_pos) { const float* t_ = pos_cur; pos_cur = pos_nxt; pos_nxt = const_cast<float*>(t_); }
   }
 

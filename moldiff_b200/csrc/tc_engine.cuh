@@ -220,7 +220,10 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 
 // sigmoid for the tensor-core path: ex2.approx + rcp.approx (~1e-6 relative), 2 MUFU + 3 FP ops
 __device__ __forceinline__ float fast_sigmoid(float x) {
-  return __frcp_rn(1.f + __expf(-x));
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
 }
 
 // byte offset of the 16-byte chunk (row r, k-chunk c) in an A plane with K columns (LBO = 128, SBO = K/8*128)

@@ -239,13 +239,20 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_fwd_kernel(cons
     // scatter_sum over row (= left): thread c owns channel c and walks the 128 CSR-ordered rows       graph.py:50
     int cur = ls[0];
     float s0 = 0.f;
-    for (int r = 0; r < tc::ROWS; ++r) {
-      const int n = ls[r];
-      if (n != cur) {
-        if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + tid, s0);
-        cur = n; s0 = 0.f;
+#pragma unroll 1
+    for (int r8 = 0; r8 < tc::ROWS; r8 += 8) {
+      float x[8];
+      int n[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { x[u] = out_tile[(r8 + u) * OUT_LD + tid]; n[u] = ls[r8 + u]; }   // 8 loads in flight
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (n[u] != cur) {
+          if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + tid, s0);
+          cur = n[u]; s0 = 0.f;
+        }
+        s0 += x[u];
       }
-      s0 += out_tile[r * OUT_LD + tid];
     }
     if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + tid, s0);
   }

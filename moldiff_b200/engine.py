@@ -117,6 +117,11 @@ KERNEL_LOGICAL_FLOP_PER_EDGE = {
                      + 2 * (256 * 64 + 64 * 64) + 64 * 256 + 64 * 256 + 256 * 256 + 256 + 129 * 32 + 32),
     # input-gradient backward of the NodeBlock per-edge Linears as autograd executes them (one dX = dY W per Linear)
     "bwd_edge_nodeblock": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
+    # tensor-core kernels: same reference Linears (as written), executed as 3 split-bf16 MMAs per product after hoisting
+    "tc_nodeblock": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
+    "tc_nodeblock_bwd": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
+    "tc_bondffn": 2.0 * (80 * 64 + 2 * (64 * 128 + 256 * 128 + 128 * 128 + 128 * 64 + 321 * 32 + 32 * 64)),
+    "tc_bondffn_bwd": 2.0 * (80 * 64 + 2 * (64 * 128 + 256 * 128 + 128 * 128 + 128 * 64 + 321 * 32 + 32 * 64)),
     "bwd_edge_bondffn": 2.0 * (80 * 64 + 2 * (64 * 128 + 256 * 128 + 128 * 128 + 128 * 64 + 321 * 32 + 32 * 64)),
 }
 

@@ -301,6 +301,8 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
         o[f"{tag}_I1"] = _t(sd[p + ".inter_module.net.0.weight"])          # [128][128]
         o[f"{tag}_G2"] = _t(sd[p + ".gate.net.3.weight"])                  # [32][64]
         o[f"{tag}_I2"] = _t(sd[p + ".inter_module.net.3.weight"])          # [128][64]
+    o["EB_SELF"] = _t(sd[eb + ".self_ffn.weight"])             # [64][64]
+    o["EB_OUT"] = _t(sd[eb + ".out_transform.weight"])         # [64][64]
     if with_backward:                                          # dX = dY @ W  with W stored [out][in] = [K][N]
         o["BT_NB_G2"] = _asis(sd[nb + ".gate.net.3.weight"])
         o["BT_NB_GE"] = _asis(g0[:, :EDGE_DIM])                # [256][64]
@@ -323,6 +325,9 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
         o["PU_PB"] = _t(sd[pb + ".bond_linear.weight"])        # [64][256]
         o["PU_PN"] = _t(sd[pb + ".node_linear.weight"])        # [64][256]
         o["PU_I1"] = _t(sd[pb + ".inter_module.net.0.weight"]) # [256][256]
+        pg = sd[pb + ".gate.net.0.weight"]                     # [32][64 + 64 + 1]
+        o["PU_GB"] = _t(pg[:, :EDGE_DIM])                      # [64][32]
+        o["PU_GN"] = _t(pg[:, EDGE_DIM:2 * EDGE_DIM])          # [64][32]
     return o
 
 
