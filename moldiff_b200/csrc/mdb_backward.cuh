@@ -225,11 +225,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_node_kernel(const BwdNodeArgs
 
   if (a.do_A) {
     const BlkOff& off = a.blkA;
-    // recompute block (i-1)'s per-node tables from its saved input
     __syncthreads();
-    load_node_tile<D>(X, a.xA, row0, a.n_nodes);
-    __syncthreads();
-    node_pre_phase(blob, off, tb, X, A, Ws, tns, row0, a.n_nodes, a.flA, a.frA, nullptr);
+    // (the per-node tables of every block were saved by the forward -- nothing to recompute here)
     // NodeBlock node tail backward: dn = W_out relu(LN(cen + agg)) + b ; h_node' = h_node + dn   graph.py:51-54,363
     store_smem<D>(dx, A, D, warp, lane);            // d(dn) = dx'  (dx itself is parked in A until reloaded below)
     {
@@ -732,20 +729,22 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     na.do_B = (i + 1 <= L - 1);
     na.do_A = (i >= 0);
     if (na.do_B) { fill_blk(na.blkB, net, i + 1); na.xB = sv.x + (size_t)(i + 1) * ND; }
+    const Tables tbi = with_block_tables(tb, sv.tabs + (size_t)(i < 0 ? 0 : i) * N * TAB_FLOATS, N);
     if (na.do_A) {
       fill_blk(na.blkA, net, i);
       na.xA = sv.x + (size_t)i * ND; na.aggA = sv.agg + (size_t)i * ND;
-      na.flA = tb.fl; na.frA = tb.fr;
+      na.tb = tbi;                      // phase A reads block i's saved centroid_lin(x) table
     }
     LAUNCH(MDB_K_bwd_node, st, (bwd_node_kernel<<<node_tiles, NTHREADS, SMEM_BWD_NODE, st>>>(na)));
     if (i < 0) break;
     fill_blk(ea.off, net, i);
-    ea.e = sv.e + (size_t)i * EC; ea.sl = sv.slsr + (size_t)i * 2 * NC; ea.fl = tb.fl; ea.fr = tb.fr;
+    ea.tb = tbi;
+    ea.e = sv.e + (size_t)i * EC; ea.sl = sv.slsr + (size_t)i * 2 * NC; ea.fl = tbi.fl; ea.fr = tbi.fr;
     LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
     if (net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_NB_G2] >= 0) {
       TcNbBwdArgs ta;
       memset(&ta, 0, sizeof(ta));
-      ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tb;
+      ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
       ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de;
@@ -758,7 +757,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     if (net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_EEH] >= 0) {
       TcFfnBwdArgs fa;
       memset(&fa, 0, sizeof(fa));
-      fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tb;
+      fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) fa.tco.o[s] = net->tc_block_off[i][s];
       fa.left = plan->left; fa.right = plan->right; fa.n_nodes = N; fa.n_edges = E;
       fa.e = ea.e; fa.dul = sv.dul; fa.dur = sv.dur; fa.dnl = sv.dnl; fa.dgn = sv.dgn;

@@ -132,7 +132,8 @@ struct NodeArgs {
   const float* blob;
   BlkOff mid, pre;      // offsets of block i (mid) and block i+1 (pre)
   HeadOff head;
-  Tables tb;
+  Tables tb;            // tables of block i (mid phase reads cen / agg)
+  Tables tb_pre;        // tables the pre phase writes for block i+1 (same buffers unless the forward saves per block)
   int n_nodes;
   int do_mid, do_pre, do_dec;   // phases
   int update_pos;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) node_kernel(const NodeArgs a) {
         if (n < a.n_nodes) reinterpret_cast<float4*>(a.x_save + (size_t)n * D)[c4] = reinterpret_cast<const float4*>(X + r * D)[c4];
       }
     }
-    node_pre_phase(blob, a.pre, tb, X, A, Ws, tns, row0, a.n_nodes, a.fl_next, a.fr_next, a.sl_next);
+    node_pre_phase(blob, a.pre, a.tb_pre, X, A, Ws, tns, row0, a.n_nodes, a.fl_next, a.fr_next, a.sl_next);
   }
 
   if (a.do_dec) {
@@ -725,6 +726,7 @@ struct Saved {
   float *x;                  // [L][N][256]  h_node entering block i
   float *agg;                // [L][N][256]  aggregated NodeBlock messages of block i
   float *slsr;               // [L][2][N][64]
+  float *tabs;               // [L][N * TAB_FLOATS]  per-node hoisted tables of every block (hn, gx, cen, nl, gn, fl, fr)
   float *dx;                 // [N][256]  running d/d h_node
   float *dh, *de;            // [E][64]   d/d h_edge (block output -> block input), d/d e
   float *dg;                 // [E][16]   d/d rbf features, summed over blocks
@@ -735,10 +737,24 @@ struct Saved {
   float *ddect;              // [N][64]
 };
 
+constexpr int TAB_FLOATS = 3 * D + 2 * 128 + 2 * 32 + 2 * C;   // per node
+
+// Tables whose per-block members (hn, gx, cen, nl, gn, fl, fr) point into one saved slab
+Tables with_block_tables(const Tables& tb, float* slab, int64_t N) {
+  Tables t = tb;
+  size_t o = 0;
+  auto take = [&](size_t n) { float* p = slab + o; o += n; return p; };
+  t.hn = take(N * D); t.gx = take(N * D); t.cen = take(N * D);
+  t.nll = take(N * 128); t.nlr = take(N * 128); t.gnl = take(N * 32); t.gnr = take(N * 32);
+  t.fl = take(N * C); t.fr = take(N * C);
+  return t;
+}
+
 size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   size_t o = 0;
   auto take = [&](size_t n) { float* p = base ? base + o : nullptr; o += al(n); return p; };
   sv.e = take(L * E * C); sv.x = take(L * N * D); sv.agg = take(L * N * D); sv.slsr = take(L * 2 * N * C);
+  sv.tabs = take(L * N * TAB_FLOATS);
   sv.dx = take(N * D); sv.dh = take(E * C); sv.de = take(E * C); sv.dg = take(E * G);
   sv.dul = take(N * C); sv.dur = take(N * C);
   sv.dagg = take(N * D); sv.dgx = take(N * D); sv.dhn = take(N * D);
@@ -802,8 +818,10 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   if (in.save) carve_saved(sv, workspace + tb_floats, N, E, L);
   const size_t NC = (size_t)N * C, ND = (size_t)N * D, EC = (size_t)E * C;
   auto sl_of = [&](int i) { return in.save ? sv.slsr + (size_t)i * 2 * NC : tb.slsr + (size_t)(i & 1) * 2 * NC; };
-  auto fl_of = [&](int i) { return tb.fl + (size_t)(i & 1) * NC; };
-  auto fr_of = [&](int i) { return tb.fr + (size_t)(i & 1) * NC; };
+  // per-block view of the hoisted tables: one shared set normally, one slab per block when saving for the backward
+  auto tb_of = [&](int i) { return in.save ? with_block_tables(tb, sv.tabs + (size_t)i * N * TAB_FLOATS, N) : tb; };
+  auto fl_of = [&](int i) { return in.save ? tb_of(i).fl : tb.fl + (size_t)(i & 1) * NC; };
+  auto fr_of = [&](int i) { return in.save ? tb_of(i).fr : tb.fr + (size_t)(i & 1) * NC; };
   HeadOff head;
   for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
   const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
@@ -825,7 +843,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   float* pos_nxt = tb.pos1;
   NodeArgs na;
   memset(&na, 0, sizeof(na));
-  na.blob = net->blob; na.head = head; na.tb = tb; na.n_nodes = N; na.update_pos = net->update_pos;
+  na.blob = net->blob; na.head = head; na.tb = tb; na.tb_pre = tb_of(0); na.n_nodes = N; na.update_pos = net->update_pos;
   na.kind = net->kind; na.kn = net->num_node_types; na.pred_node = in.out_node;
   // pre(0)
   fill_blk(na.pre, net, 0);
@@ -842,6 +860,8 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 
   for (int i = 0; i < L; ++i) {
     fill_blk(ea.off, net, i);
+    const Tables tbi = tb_of(i);
+    ea.tb = tbi;
     ea.sl = sl_of(i); ea.fl = fl_of(i); ea.fr = fr_of(i); ea.ebuf = in.save ? sv.e + (size_t)i * EC : tb.ebuf;
     ea.pos_cur = pos_cur; ea.pos_nxt = pos_nxt;
     const bool tc_nb = net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_NB_EN1] >= 0;
@@ -850,7 +870,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     if (E > 0 && tc_ffn) {
       TcFfnArgs fa;
       memset(&fa, 0, sizeof(fa));
-      fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tb;
+      fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) fa.tco.o[s] = net->tc_block_off[i][s];
       fa.left = plan->left; fa.right = plan->right; fa.n_nodes = N; fa.n_edges = E;
       fa.pos = pos_cur; fa.rbf_lo = net->rbf_start; fa.rbf_hi = net->rbf_stop; fa.ebuf = ea.ebuf; fa.sl = ea.sl;
@@ -863,7 +883,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     if (E > 0 && tc_nb) {
       TcNbArgs ta;
       memset(&ta, 0, sizeof(ta));
-      ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tb;
+      ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
       ta.dbg = g_dbg_stamps;
@@ -872,9 +892,10 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
              (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
     }
     fill_blk(na.mid, net, i);
+    na.tb = tbi; na.tb_pre = tb_of(i + 1 < L ? i + 1 : i);
     na.do_mid = 1; na.do_pre = (i + 1 < L); na.do_dec = (i + 1 == L) && net->kind != 0;
     if (na.do_pre) fill_blk(na.pre, net, i + 1);
-    na.sl_next = sl_of(i + 1 < L ? i + 1 : i); na.fl_next = fl_of(i + 1); na.fr_next = fr_of(i + 1);
+    na.sl_next = sl_of(i + 1 < L ? i + 1 : i); na.fl_next = fl_of(i + 1 < L ? i + 1 : i); na.fr_next = fr_of(i + 1 < L ? i + 1 : i);
     na.x_save = (in.save && i + 1 < L) ? sv.x + (size_t)(i + 1) * ND : nullptr;
     na.agg_save = in.save ? sv.agg + (size_t)i * ND : nullptr;
     na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
@@ -882,7 +903,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     if (E > 0 && tc_nb && net->tc_block_off[i][MDB_T_EB_SELF] >= 0) {
       TcEdgeDArgs da;
       memset(&da, 0, sizeof(da));
-      da.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); da.tb = tb;
+      da.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); da.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) da.tco.o[s] = net->tc_block_off[i][s];
       da.left = plan->left; da.right = plan->right; da.n_nodes = N; da.n_edges = E; da.update_pos = net->update_pos;
       da.ebuf = ea.ebuf; da.sl = ea.sl; da.fl = ea.fl; da.fr = ea.fr; da.pos_cur = pos_cur; da.pos_nxt = pos_nxt;
