@@ -321,6 +321,7 @@ __device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restr
     }
   };
   float s = 0.f;
+#pragma unroll 1
   for (int c0 = 0; c0 < 128; c0 += 32) {
     float a[32];
     pre(c0, a);
@@ -329,6 +330,7 @@ __device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restr
   }
   const float m_h = s * (1.f / 128.f);
   float q = 0.f;
+#pragma unroll 1
   for (int c0 = 0; c0 < 128; c0 += 32) {
     float a[32];
     pre(c0, a);
@@ -504,7 +506,21 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_nodeblock_bwd_kernel(cons
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), D1, false, true, true);
   if (p.role == 0) {
     tc::rows_wait_acc(p);
-    ln_bwd_half<false, true>(lane_base + D1 + hc, nullptr, gxr, a.v.g1_g + hc, a.v.g1_be + hc, dr, stat, row, half);
+    // a3 = acc + gx[r]: fold the gathered row into the accumulator ONCE (TMEM read-modify-write) instead of
+    // re-gathering it in each of the four LayerNorm-backward passes
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float t32[32];
+      tc::tmem_ld32(lane_base + D1 + hc + c0, t32);
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(gxr + c0 + i);
+        t32[i] += x.x; t32[i + 1] += x.y; t32[i + 2] += x.z; t32[i + 3] += x.w;
+      }
+      tc::tmem_st32(lane_base + D1 + hc + c0, t32);
+    }
+    tc::tmem_st_wait();
+    ln_bwd_half<false, false>(lane_base + D1 + hc, nullptr, nullptr, a.v.g1_g + hc, a.v.g1_be + hc, dr, stat, row, half);
     if (valid) {
       float* dst = a.dgx + (size_t)rr * D + hc;
 #pragma unroll
