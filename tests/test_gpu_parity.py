@@ -289,3 +289,63 @@ def test_fp32_ffma_path_still_matches(seeded_models, dev, monkeypatch):
     out = cuda_moldiff(model, inp, dev)
     for k in ref:
         assert R.rel_err(out[k], ref[k]) < 2e-5, k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full single-GPU sizes (no oracle needed)
+# ---------------------------------------------------------------------------------------------------------
+def _random_rotation(seed):
+    g = torch.Generator().manual_seed(seed)
+    q, r = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    q = q * torch.sign(torch.diagonal(r))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+@pytest.mark.parametrize("B,max_size", [(256, None), (512, 29)])
+def test_e3_equivariance_and_batch_independence_full_size(B, max_size, gpu_models, dev):
+    """Config 2 size (B=256, N=6 286, E=157 102) and a QM9-shaped dense batch: rotating + translating the input
+    positions must rotate + translate pred_pos and leave the type logits unchanged (the network only sees relative
+    vectors and distances, graph.py:369-374,393); and a molecule's outputs must not depend on its batch mates."""
+    model = gpu_models[0]
+    inp = batch_inputs(B=B, seed_graph=2023, seed_inputs=7, t_values=(900, 500, 100), max_size=max_size)
+    d = to_dev(inp, dev)
+    ei, be, he = doubled(d)
+    rot = _random_rotation(5).to(dev)
+    shift = torch.tensor([1.5, -2.0, 0.7], device=dev)
+    with torch.no_grad():
+        a = model(d["h_node"], d["pos"], d["batch_node"], he, ei, be, d["t"])
+        b = model(d["h_node"], d["pos"] @ rot.T + shift, d["batch_node"], he, ei, be, d["t"])
+    for v in a.values():
+        assert torch.isfinite(v).all()
+    assert R.rel_err((a["pred_pos"] @ rot.T + shift).cpu(), b["pred_pos"].cpu()) < TOL
+    assert R.rel_err(b["pred_node"].cpu(), a["pred_node"].cpu()) < TOL
+    assert R.rel_err(b["pred_halfedge"].cpu(), a["pred_halfedge"].cpu()) < TOL
+    # the first 3 molecules alone (same graphs, same inputs) must reproduce their slice of the big batch
+    small = batch_inputs(B=B, seed_graph=2023, seed_inputs=7, t_values=(900, 500, 100), max_size=max_size)
+    n3 = int((small["batch_node"] < 3).sum())
+    e3 = int((small["batch_halfedge"] < 3).sum())
+    sub = dict(batch_node=small["batch_node"][:n3], halfedge_index=small["halfedge_index"][:, :e3],
+               batch_halfedge=small["batch_halfedge"][:e3], h_node=small["h_node"][:n3], h_half=small["h_half"][:e3],
+               pos=small["pos"][:n3], t=small["t"][:3])
+    c = cuda_moldiff(model, sub, dev)
+    assert R.rel_err(c["pred_pos"], a["pred_pos"][:n3].cpu()) < TOL
+    assert R.rel_err(c["pred_node"], a["pred_node"][:n3].cpu()) < TOL
+    assert R.rel_err(c["pred_halfedge"], a["pred_halfedge"][:e3].cpu()) < TOL
+
+
+def test_train_config_size_forward_and_loss(gpu_models, dev):
+    """BASELINE config 3 shape: get_loss forward at batch_size=1024 (N ~ 25k, E ~ 614k) returns finite losses."""
+    from moldiff_b200.placeholder import make_data_placeholder
+    np.random.seed(2023)
+    ph = make_data_placeholder(1024, device=dev)
+    g = torch.Generator().manual_seed(3)
+    N, Eh = len(ph["batch_node"]), len(ph["batch_halfedge"])
+    node_type = torch.randint(0, 7, (N,), generator=g).to(dev)
+    half_type = torch.randint(0, 5, (Eh,), generator=g).to(dev)
+    pos = torch.randn(N, 3, generator=g).to(dev)
+    torch.manual_seed(11)
+    out = gpu_models[0].get_loss(node_type, pos, ph["batch_node"], half_type, ph["halfedge_index"], ph["batch_halfedge"], 1024)
+    assert set(out) == {"loss", "loss_pos", "loss_node", "loss_edge"}
+    assert all(torch.isfinite(v) for v in out.values())
