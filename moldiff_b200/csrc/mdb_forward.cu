@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -665,6 +666,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_nodeblock.cuh"
 #include "tc_bondffn.cuh"
 #include "tc_edge_d.cuh"
+#include "tc_nodeblock16.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -782,6 +784,7 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
+  CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
   done = true;
   return MDB_OK;
 }
@@ -888,8 +891,14 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
       ta.dbg = g_dbg_stamps;
       fill_nb_vecs(ta.v, net->blob_host, ea.off);
-      LAUNCH(MDB_K_tc_nodeblock, st,
-             (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
+      static const bool nb16 = []() { const char* e = getenv("MDB_TC_NB16"); return e == nullptr || e[0] != '0'; }();
+      if (nb16) {
+        LAUNCH(MDB_K_tc_nodeblock, st,
+               (tc_nodeblock_fwd16_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, NB16_THREADS, SMEM_TC_NB16, st>>>(ta)));
+      } else {
+        LAUNCH(MDB_K_tc_nodeblock, st,
+               (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
+      }
     }
     fill_blk(na.mid, net, i);
     na.tb = tbi; na.tb_pre = tb_of(i + 1 < L ? i + 1 : i);

@@ -20,27 +20,31 @@ constexpr int KB = 16;                 // K columns per weight stage
 constexpr int NSTAGE = 4;
 constexpr uint32_t STAGE_SLOT = 256 * KB * 2 * 2;   // bytes reserved per stage (N = 256 worst case): 32 KB
 
-struct PipeSmem {                      // lives in shared memory
-  uint64_t full[NSTAGE], empty[NSTAGE], done, a_ready;
+template <int NS>
+struct PipeSmemT {                     // lives in shared memory
+  uint64_t full[NS], empty[NS], done, a_ready;
   uint32_t tmem_base;
 };
+using PipeSmem = PipeSmemT<NSTAGE>;
 
-struct Pipe {
-  PipeSmem* s;
+template <int NS>
+struct PipeT {
+  PipeSmemT<NS>* s;
   uint8_t* stages;      // NSTAGE * STAGE_SLOT, 128-byte aligned
   uint32_t it;          // running stage counter (producer and MMA thread each advance their own copy)
   uint32_t n_done;      // GEMMs completed (MMA thread / row threads)
   uint32_t n_ready;     // a_ready phases consumed (MMA thread)
   int role;             // 0 = row thread, 1 = producer thread, 2 = MMA thread, 3 = idle lane
 };
+using Pipe = PipeT<NSTAGE>;
 
-template <int NRW = 4>   // number of row warps (4: one thread per row; 8: two threads per row, split by column half)
-__device__ __forceinline__ void pipe_init(Pipe& p, PipeSmem* s, uint8_t* stages) {
+template <int NRW = 4, int NS = NSTAGE>   // NRW row warps: 4 = one thread per row, 8 / 16 = two / four threads per row
+__device__ __forceinline__ void pipe_init(PipeT<NS>& p, PipeSmemT<NS>* s, uint8_t* stages) {
   p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   p.role = warp < NRW ? 0 : (lane == 0 ? (warp == NRW ? 1 : 2) : 3);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&s->full[i], 1); mbar_init(&s->empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&s->full[i], 1); mbar_init(&s->empty[i], 1); }
     mbar_init(&s->done, 1);
     mbar_init(&s->a_ready, NRW * 32);
     fence_barrier_init();
@@ -48,13 +52,15 @@ __device__ __forceinline__ void pipe_init(Pipe& p, PipeSmem* s, uint8_t* stages)
 }
 
 // Row threads: "my part of the A planes is written and I no longer read the accumulator".
-__device__ __forceinline__ void rows_publish(Pipe& p) {
+template <int NS>
+__device__ __forceinline__ void rows_publish(PipeT<NS>& p) {
   fence_proxy_async();
   fence_before_sync();
   mbar_arrive(&p.s->a_ready);
 }
 // Row threads: wait for the accumulator of the next GEMM in program order.
-__device__ __forceinline__ void rows_wait_acc(Pipe& p) {
+template <int NS>
+__device__ __forceinline__ void rows_wait_acc(PipeT<NS>& p) {
   mbar_wait(&p.s->done, p.n_done & 1);
   ++p.n_done;
   fence_after_sync();
@@ -63,15 +69,15 @@ __device__ __forceinline__ void rows_wait_acc(Pipe& p) {
 // One GEMM: D[tmem col d_col .. +N) (+)= A(a_hi, a_lo planes, K columns) * W (image at w_img).
 // Called by ALL threads of the CTA at the same program point; row threads return immediately.
 // wait_ready = false chains a second GEMM onto the same A planes / accumulator epoch without a new a_ready phase.
-template <int K, int N>
-__device__ __forceinline__ void gemm(Pipe& p, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_img,
+template <int K, int N, int NSLOT>
+__device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_img,
                                      uint32_t d_col, bool accumulate, bool wait_ready, bool signal_done) {
   using WS = WStage<N, KB>;
   constexpr int NS = K / KB;
   static_assert(K % KB == 0, "K must be a multiple of the stage depth");
   if (p.role == 1) {
     for (int s = 0; s < NS; ++s, ++p.it) {
-      const uint32_t slot = p.it % NSTAGE, ph = (p.it / NSTAGE) & 1;
+      const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->empty[slot], ph ^ 1);
       mbar_arrive_expect_tx(&p.s->full[slot], WS::STAGE_BYTES);
       bulk_g2s(p.stages + slot * STAGE_SLOT, w_img + (size_t)s * WS::STAGE_BYTES, WS::STAGE_BYTES, &p.s->full[slot]);
@@ -87,7 +93,7 @@ __device__ __forceinline__ void gemm(Pipe& p, const uint8_t* a_hi, const uint8_t
     const uint32_t d_tmem = p.s->tmem_base + d_col;
     const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
     for (int s = 0; s < NS; ++s, ++p.it) {
-      const uint32_t slot = p.it % NSTAGE, ph = (p.it / NSTAGE) & 1;
+      const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->full[slot], ph);
       fence_after_sync();
       const uint32_t bhi = smem_u32(p.stages + slot * STAGE_SLOT), blo = bhi + WS::PLANE_BYTES;
