@@ -114,13 +114,26 @@ enum mdb_head_slot {
   X(ER_BL) X(ER_GB) X(ER_I1) X(ER_G2) X(ER_I2)              /* bond_ffn_right                        */ \
   X(BT_EEH) X(BT_EEG)                                       /* edge_embs, transposed use (backward)  */ \
   X(BT_EL_G2) X(BT_EL_I2) X(BT_EL_GB) X(BT_EL_I1) X(BT_EL_BL) /* bond_ffn_left, transposed use       */ \
-  X(BT_ER_G2) X(BT_ER_I2) X(BT_ER_GB) X(BT_ER_I1) X(BT_ER_BL)
+  X(BT_ER_G2) X(BT_ER_I2) X(BT_ER_GB) X(BT_ER_I1) X(BT_ER_BL)                                      \
+  /* per-node Linears (tc_node_kernel): NodeBlock node path, PosUpdate node MLPs, hoisted projections */ \
+  X(NB_OUT) X(PU_LL1) X(PU_LL2) X(PU_RL1) X(PU_RL2) X(NB_NN1) X(NB_NN2) X(NB_GX) X(NB_CEN)         \
+  X(EL_NL) X(ER_NL) X(EL_GN) X(ER_GN) X(EB_NFL) X(EB_NFR)
 
 enum mdb_tc_slot {
 #define MDB_X(name) MDB_T_##name,
   MDB_TC_SLOTS(MDB_X)
 #undef MDB_X
   MDB_NUM_TC_SLOTS
+};
+
+/* Tensor-core images of the head Linears applied per node (decoders). */
+#define MDB_TC_HEAD_SLOTS(X) X(NDEC1) X(NDEC2) X(EDEC1N)
+
+enum mdb_tc_head_slot {
+#define MDB_X(name) MDB_TH_##name,
+  MDB_TC_HEAD_SLOTS(MDB_X)
+#undef MDB_X
+  MDB_NUM_TC_HEAD_SLOTS
 };
 
 /* Static description of one packed network (host struct, passed by pointer). */
@@ -140,6 +153,7 @@ typedef struct mdb_net_desc {
                                 /* kernels by value, i.e. through the constant bank); required when tc_blob set  */
   const void* tc_blob;          /* device: tensor-core operand images, or NULL = fp32 FFMA path only    */
   int64_t tc_block_off[MDB_MAX_BLOCKS][MDB_NUM_TC_SLOTS];      /* byte offsets into tc_blob, -1 = absent */
+  int64_t tc_head_off[MDB_NUM_TC_HEAD_SLOTS];
 } mdb_net_desc;
 
 /*
@@ -200,7 +214,7 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
   X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
-  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd)
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,

@@ -667,6 +667,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_bondffn.cuh"
 #include "tc_edge_d.cuh"
 #include "tc_nodeblock16.cuh"
+#include "tc_node.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -785,6 +786,7 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
+  CUDA_TRY(cudaFuncSetAttribute(tc_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NODE));
   done = true;
   return MDB_OK;
 }
@@ -800,6 +802,36 @@ struct FwdIn {
   float *out_node, *out_pos, *out_edge;        // kind 0: h_node/pos/h_edge; kind 1: preds; kind 2: logits in out_edge
   int save;                                    // keep per-block inputs for the backward pass
 };
+
+// node kernel launch: tensor-core version when its operand images are packed, FFMA version otherwise
+int launch_node(const mdb_net_desc* net, const NodeArgs& na, int blk_mid, int blk_pre, int node_tiles, cudaStream_t st) {
+  static const bool tc_node_on = []() { const char* e = getenv("MDB_TC_NODE"); return e == nullptr || e[0] != '0'; }();
+  const int ref_blk = blk_pre >= 0 ? blk_pre : blk_mid;
+  const bool tc = tc_node_on && net->tc_blob != nullptr && net->blob_host != nullptr && ref_blk >= 0 &&
+                  net->tc_block_off[ref_blk][MDB_T_NB_OUT] >= 0;
+  if (!tc) {
+    LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
+    return MDB_OK;
+  }
+  TcNodeArgs ta;
+  memset(&ta, 0, sizeof(ta));
+  ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob);
+  for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) {
+    ta.mid.o[s] = blk_mid >= 0 ? net->tc_block_off[blk_mid][s] : -1;
+    ta.pre.o[s] = blk_pre >= 0 ? net->tc_block_off[blk_pre][s] : -1;
+  }
+  for (int s = 0; s < MDB_NUM_TC_HEAD_SLOTS; ++s) ta.hd.o[s] = net->tc_head_off[s];
+  ta.tb = na.tb; ta.tb_pre = na.tb_pre; ta.n_nodes = na.n_nodes;
+  ta.do_mid = na.do_mid; ta.do_pre = na.do_pre; ta.do_dec = na.do_dec; ta.update_pos = na.update_pos;
+  ta.kind = na.kind; ta.kn = na.kn;
+  ta.sl_next = na.sl_next; ta.fl_next = na.fl_next; ta.fr_next = na.fr_next; ta.x_save = na.x_save; ta.agg_save = na.agg_save;
+  ta.pos_cur = na.pos_cur; ta.pos_nxt = na.pos_nxt; ta.pred_node = na.pred_node;
+  fill_node_vecs(ta.v, net->blob_host, na.do_mid ? &na.mid : nullptr, na.do_pre ? &na.pre : nullptr,
+                 na.do_dec ? &na.head : nullptr, na.kind, na.update_pos != 0);
+  LAUNCH(MDB_K_tc_node, st,
+         (tc_node_kernel<<<(na.n_nodes + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NODE, st>>>(ta)));
+  return MDB_OK;
+}
 
 int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, float* workspace,
                 size_t workspace_bytes, cudaStream_t st) {
@@ -853,7 +885,8 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   na.do_mid = 0; na.do_pre = 1; na.do_dec = 0; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
   na.sl_next = sl_of(0); na.fl_next = fl_of(0); na.fr_next = fr_of(0);
   na.x_save = in.save ? sv.x : nullptr; na.agg_save = nullptr;
-  LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
+  rc = launch_node(net, na, -1, 0, node_tiles, st);
+  if (rc) return rc;
 
   EdgeArgs ea;
   memset(&ea, 0, sizeof(ea));
@@ -908,7 +941,8 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     na.x_save = (in.save && i + 1 < L) ? sv.x + (size_t)(i + 1) * ND : nullptr;
     na.agg_save = in.save ? sv.agg + (size_t)i * ND : nullptr;
     na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
-    LAUNCH(MDB_K_node, st, (node_kernel<<<node_tiles, NTHREADS, SMEM_NODE, st>>>(na)));
+    rc = launch_node(net, na, i, na.do_pre ? i + 1 : -1, node_tiles, st);
+    if (rc) return rc;
     if (E > 0 && tc_nb && net->tc_block_off[i][MDB_T_EB_SELF] >= 0) {
       TcEdgeDArgs da;
       memset(&da, 0, sizeof(da));

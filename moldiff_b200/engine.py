@@ -21,6 +21,7 @@ _lib_lock = threading.Lock()
 NUM_HEAD = len(packing.HEAD_SLOTS)
 NUM_BLOCK = len(packing.BLOCK_SLOTS)
 NUM_TC = len(packing.TC_SLOTS)
+NUM_TC_HEAD = len(packing.TC_HEAD_SLOTS)
 MAX_BLOCKS = packing.MAX_BLOCKS
 
 
@@ -41,6 +42,7 @@ class NetDesc(C.Structure):
         ("blob_host", C.c_void_p),
         ("tc_blob", C.c_void_p),
         ("tc_block_off", (C.c_int64 * NUM_TC) * MAX_BLOCKS),
+        ("tc_head_off", C.c_int64 * NUM_TC_HEAD),
     ]
 
 
@@ -204,14 +206,18 @@ class PackedNet:
         for b in range(MAX_BLOCKS):
             for s in range(NUM_TC):
                 d.tc_block_off[b][s] = -1
+        for s in range(NUM_TC_HEAD):
+            d.tc_head_off[s] = -1
         if os.environ.get("MDB_DISABLE_TC", "0") != "1":
-            tcb, tco = packing.pack_tc(state_dict, net_prefix=net_prefix, num_blocks=num_blocks,
-                                       update_pos=update_pos, with_backward=(kind == 2))
+            tcb, tco, tch = packing.pack_tc(state_dict, net_prefix=net_prefix, num_blocks=num_blocks,
+                                            update_pos=update_pos, with_backward=(kind == 2), kind=kind)
             self.tc_blob = tcb.to(self.device)
             d.tc_blob = self.tc_blob.data_ptr()
             for b in range(num_blocks):
                 for s in range(NUM_TC):
                     d.tc_block_off[b][s] = tco[b][s]
+            for s in range(NUM_TC_HEAD):
+                d.tc_head_off[s] = tch[s]
         self.desc = d
         self.kind = kind
         self.num_blocks = num_blocks

@@ -30,6 +30,7 @@ def _parse_slots(macro):
 
 BLOCK_SLOTS = _parse_slots("MDB_BLOCK_SLOTS")
 TC_SLOTS = _parse_slots("MDB_TC_SLOTS")
+TC_HEAD_SLOTS = re.findall(r"X\((\w+)\)", re.search(r"#define\s+MDB_TC_HEAD_SLOTS\(X\)(.*)", open(_HEADER).read()).group(1))
 HEAD_SLOTS = _parse_slots("MDB_HEAD_SLOTS")
 
 
@@ -301,6 +302,25 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
         o[f"{tag}_I1"] = _t(sd[p + ".inter_module.net.0.weight"])          # [128][128]
         o[f"{tag}_G2"] = _t(sd[p + ".gate.net.3.weight"])                  # [32][64]
         o[f"{tag}_I2"] = _t(sd[p + ".inter_module.net.3.weight"])          # [128][64]
+    # per-node Linears (tc_node_kernel)
+    o["NB_OUT"] = _t(sd[nb + ".out_transform.weight"])
+    o["NB_NN1"] = _t(sd[nb + ".node_net.net.0.weight"])
+    o["NB_NN2"] = _t(sd[nb + ".node_net.net.3.weight"])
+    o["NB_GX"] = _t(g0[:, EDGE_DIM:EDGE_DIM + NODE_DIM])
+    o["NB_CEN"] = _t(sd[nb + ".centroid_lin.weight"])
+    for tag, sub in (("EL", "bond_ffn_left"), ("ER", "bond_ffn_right")):
+        p = f"{eb}.{sub}"
+        gw = sd[p + ".gate.net.0.weight"]
+        o[f"{tag}_NL"] = _t(sd[p + ".node_linear.weight"])                 # [256][128]
+        o[f"{tag}_GN"] = _t(gw[:, EDGE_DIM:EDGE_DIM + NODE_DIM])           # [256][32]
+    o["EB_NFL"] = _t(sd[eb + ".node_ffn_left.weight"])         # [256][64]
+    o["EB_NFR"] = _t(sd[eb + ".node_ffn_right.weight"])
+    if update_pos:
+        pp = f"{net_prefix}.pos_blocks.{i}"
+        o["PU_LL1"] = _t(sd[pp + ".left_lin_edge.net.0.weight"])   # [256][64]
+        o["PU_LL2"] = _t(sd[pp + ".left_lin_edge.net.3.weight"])   # [64][64]
+        o["PU_RL1"] = _t(sd[pp + ".right_lin_edge.net.0.weight"])
+        o["PU_RL2"] = _t(sd[pp + ".right_lin_edge.net.3.weight"])
     o["EB_SELF"] = _t(sd[eb + ".self_ffn.weight"])             # [64][64]
     o["EB_OUT"] = _t(sd[eb + ".out_transform.weight"])         # [64][64]
     if with_backward:                                          # dX = dY @ W  with W stored [out][in] = [K][N]
@@ -331,8 +351,18 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
     return o
 
 
-def pack_tc(sd, *, net_prefix, num_blocks, update_pos, with_backward):
-    """Returns (int16 1-D CPU tensor, block_off list[list[int]] in BYTES, -1 = absent); images 128-byte aligned."""
+def tc_head_tensors(sd, kind):
+    if kind == 1:
+        return {"NDEC1": _t(sd["node_decoder.net.0.weight"]),
+                "NDEC2": _pad_cols(_t(sd["node_decoder.net.3.weight"]), 32)}
+    if kind == 2:
+        return {"EDEC1N": _t(sd["edge_decoder.net.0.weight"][:, EDGE_DIM:])}       # [256][64]
+    return {}
+
+
+def pack_tc(sd, *, net_prefix, num_blocks, update_pos, with_backward, kind=0):
+    """Returns (int16 1-D CPU tensor, block_off list[list[int]] in BYTES, head_off list[int]); -1 = absent;
+    images 128-byte aligned."""
     chunks, cursor, offs = [], 0, []
     for i in range(num_blocks):
         bt = tc_block_tensors(sd, net_prefix, i, update_pos, with_backward)
@@ -349,4 +379,17 @@ def pack_tc(sd, *, net_prefix, num_blocks, update_pos, with_backward):
                 chunks.append(torch.zeros(pad, dtype=torch.int16))
             cursor += img.numel() + pad
         offs.append(row)
-    return torch.cat(chunks), offs
+    ht = tc_head_tensors(sd, kind)
+    head = []
+    for name in TC_HEAD_SLOTS:
+        if name not in ht:
+            head.append(-1)
+            continue
+        img = tc_image(ht[name])
+        pad = (-img.numel()) % 64
+        head.append(cursor * 2)
+        chunks.append(img)
+        if pad:
+            chunks.append(torch.zeros(pad, dtype=torch.int16))
+        cursor += img.numel() + pad
+    return torch.cat(chunks), offs, head
