@@ -8,8 +8,9 @@
 //   * W: pre-packed on the host (moldiff_b200/packing.py: tc_images) as per-K-stage images of the
 //     "N x K, K-major" B operand in the same canonical layout, hi plane then lo plane, so that one
 //     cp.async.bulk per plane brings a stage in.
-//   * fp32 parity: split-bf16, three MMAs per K step accumulate hi*hi + lo*hi + hi*lo into the same TMEM tile
-//     (1.7e-5 end-to-end vs the 1e-4 bar; single-pass bf16 is 1e-2).
+//   * fp32 parity: split operands x = hi (bf16) + lo (fp16), three MMAs per K step accumulate hi*hi + lo*hi + hi*lo
+//     into the same fp32 TMEM tile (a bf16/bf16 split gives 1.7e-5 end-to-end vs the 1e-4 bar, single-pass
+//     bf16 1e-2; the fp16 lo plane buys ~8x more at the same cost).
 //   * D: TMEM, lane = row, column = n (fp32).  Read back with tcgen05.ld 32x32b (thread t of warp w owns lane
 //     32 * (w % 4) + t).
 #pragma once
@@ -86,9 +87,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   return d;
 }
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor, kind::f16: D fp32, both operands K-major, M x N.  a_fmt / b_fmt: 0 = fp16, 1 = bf16
+// (independent fields: the hi planes are bf16, the lo planes fp16 -- see split8).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]   -- issued by ONE thread
@@ -199,10 +201,18 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 // ---- split-bf16 helpers -----------------------------------------------------------------------------------
 // 8 consecutive k values of one row -> one 16-byte chunk in the hi plane and one in the lo plane.
-// cvt.rn.bf16x2.f32 (F2FP, full rate) packs two values per instruction; the scalar cvt (F2F) is quarter rate.
+// cvt.rn.{bf16x2,f16x2}.f32 (F2FP, full rate) pack two values per instruction; the scalar cvt (F2F) is quarter rate.
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));   // first source -> upper half
+  return r;
+}
+// Split: hi = bf16(x) keeps fp32's exponent range; lo = fp16(x - hi) carries 11 more mantissa bits (|lo| <= 2^-9 |x|
+// sits comfortably inside fp16's range for O(1e-3 .. 1e4) activations; below 6e-5 fp16 goes subnormal, an absolute
+// error of < 3e-8).  hi + lo reproduces x to ~2^-20 instead of 2^-17 with a bf16 lo, at the same cost.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
@@ -212,7 +222,7 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
     const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);            // exact: bf16 -> fp32 is a 16-bit shift
     const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
-    l[i] = pack_bf16x2(r0, r1);
+    l[i] = pack_f16x2(r0, r1);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

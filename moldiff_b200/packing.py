@@ -254,9 +254,10 @@ TC_KB = 16   # K columns per weight stage; must equal tc::KB in csrc/tc_pipe.cuh
 
 
 def split_bf16(w):
-    """fp32 -> (hi, lo) bf16 pair with hi + lo ~= w to ~2^-17 relative (round-to-nearest-even both times)."""
+    """fp32 -> (hi bf16, lo fp16) with hi + lo ~= w to ~2^-20 relative (round-to-nearest-even both times): bf16 keeps
+    the exponent range, the fp16 remainder (|lo| <= 2^-9 |w|) adds 11 mantissa bits.  Both are 16-bit planes."""
     hi = w.to(torch.bfloat16)
-    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
     return hi, lo
 
 
@@ -276,9 +277,9 @@ def tc_image(w_kn):
     parts = []
     for s in range(k // TC_KB):
         sl = slice(s * TC_KB, (s + 1) * TC_KB)
-        parts.append(_canonical_plane(hi[:, sl]))
-        parts.append(_canonical_plane(lo[:, sl]))
-    return torch.cat(parts).view(torch.int16)
+        parts.append(_canonical_plane(hi[:, sl]).view(torch.int16))
+        parts.append(_canonical_plane(lo[:, sl]).view(torch.int16))
+    return torch.cat(parts)
 
 
 def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):

@@ -183,7 +183,8 @@ def test_packing_roundtrip_and_tc_images(seeded_models):
     assert torch.equal(blob[o:o + 256 * 256].reshape(256, 256), w.t())
     assert all(x % 32 == 0 for row in block_off for x in row if x >= 0)           # 128-byte aligned slots
     img = packing.tc_image(w.t().contiguous())
-    hi, lo = packing.split_bf16(w)                                                 # [N][K]
+    hi, lo = packing.split_bf16(w)                                                 # [N][K] bf16 / fp16
+    assert float((hi.float() + lo.float() - w).abs().max() / w.abs().max()) < 2e-6
     assert img.numel() == 2 * 256 * 256
     # element (n, k) of stage s = k // KB sits at (n%8)*8 + (n//8)*(KB//8)*64 + ((k%KB)//8)*64 + k%8  (int16 units)
     KB = packing.TC_KB
@@ -192,7 +193,8 @@ def test_packing_roundtrip_and_tc_images(seeded_models):
     base = s * 2 * 256 * KB
     idx = base + (n % 8) * 8 + (n // 8) * (KB // 8) * 64 + (kk // 8) * 64 + kk % 8
     assert img[idx] == hi[n, k].view(torch.int16) and img[idx + 256 * KB] == lo[n, k].view(torch.int16)
-    tcb, tco = packing.pack_tc(sd, net_prefix="denoiser", num_blocks=6, update_pos=True, with_backward=False)
+    tcb, tco, tch = packing.pack_tc(sd, net_prefix="denoiser", num_blocks=6, update_pos=True, with_backward=False, kind=1)
+    assert all(x % 128 == 0 for x in tch if x >= 0) and tch[0] >= 0
     assert all(x % 128 == 0 for row in tco for x in row if x >= 0)
 
 
