@@ -39,7 +39,7 @@ __device__ __forceinline__ void load_cols_tm(uint32_t taddr, float (&v)[NC]) {
     tc::tmem_ld32_issue(taddr + 32, r1);
     tc::tmem_ld32_wait(r0); tc::tmem_ld32_wait(r1);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+    for (int i = 0; i < 32; ++i) { v[i] = tc::acc_f(r0[i]); v[32 + i] = tc::acc_f(r1[i]); }
   }
 }
 

@@ -8,9 +8,9 @@
 //   * W: pre-packed on the host (moldiff_b200/packing.py: tc_images) as per-K-stage images of the
 //     "N x K, K-major" B operand in the same canonical layout, hi plane then lo plane, so that one
 //     cp.async.bulk per plane brings a stage in.
-//   * fp32 parity: split operands x = hi (bf16) + lo (fp16), three MMAs per K step accumulate hi*hi + lo*hi + hi*lo
+//   * fp32 parity: split operands x = hi + lo (two fp16 planes), three MMAs per K step accumulate hi*hi + lo*hi + hi*lo
 //     into the same fp32 TMEM tile (a bf16/bf16 split gives 1.7e-5 end-to-end vs the 1e-4 bar, single-pass
-//     bf16 1e-2; the fp16 lo plane buys ~8x more at the same cost).
+//     bf16 1e-2; fp16 planes carry 22 bits for the same cost).
 //   * D: TMEM, lane = row, column = n (fp32).  Read back with tcgen05.ld 32x32b (thread t of warp w owns lane
 //     32 * (w % 4) + t).
 #pragma once
@@ -87,8 +87,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)1 << 46;
   return d;
 }
-// Instruction descriptor, kind::f16: D fp32, both operands K-major, M x N.  a_fmt / b_fmt: 0 = fp16, 1 = bf16
-// (independent fields: the hi planes are bf16, the lo planes fp16 -- see split8).
+// Instruction descriptor, kind::f16: D fp32, both operands K-major, M x N.  a_fmt / b_fmt: 0 = fp16, 1 = bf16; the two
+// must be equal on sm_100a (see split8).
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_fmt, uint32_t b_fmt) {
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -108,6 +108,14 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+
+// Weight images are stored multiplied by ACC_SCALE (packing.tc_image): an nn.Linear weight is O(1/sqrt(K)) ~ 0.03, whose
+// fp16 remainder plane would sit in the subnormal range (20 significant bits); x256 puts |w| >= 5e-4 at the full 22.
+// TMEM accumulators therefore hold ACC_SCALE x the logical value: every TMEM read multiplies by 1 / ACC_SCALE (exact,
+// and contracted into the bias FFMA that follows), every TMEM write by ACC_SCALE.
+constexpr float ACC_SCALE = 256.f;
+constexpr float ACC_UNSCALE = 1.f / 256.f;
+__device__ __forceinline__ float acc_f(uint32_t r) { return __uint_as_float(r) * ACC_UNSCALE; }
 
 // ---- TMEM -> registers: 32 consecutive fp32 columns of this thread's lane ------------------------------
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -130,7 +138,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
                :
                : "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = acc_f(r[i]);
 }
 
 // Split issue / wait so that the next chunk's TMEM read overlaps the math on the current one.  The wait takes the
@@ -173,11 +181,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
                :
                : "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = acc_f(r[i]);
 }
 
 // registers -> TMEM: 32 consecutive fp32 columns of this thread's lane (used to park fp32 tiles between GEMMs)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&w)[32]) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = w[i] * ACC_SCALE;
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -207,22 +218,44 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));   // first source -> upper half
   return r;
 }
-// Split: hi = bf16(x) keeps fp32's exponent range; lo = fp16(x - hi) carries 11 more mantissa bits (|lo| <= 2^-9 |x|
-// sits comfortably inside fp16's range for O(1e-3 .. 1e4) activations; below 6e-5 fp16 goes subnormal, an absolute
-// error of < 3e-8).  hi + lo reproduces x to ~2^-20 instead of 2^-17 with a bf16 lo, at the same cost.
+// Operand split.  tcgen05 kind::f16 wants A and B in the SAME 16-bit format (a bf16 x fp16 pair traps as an illegal
+// instruction on sm_100a), so the choice is global:
+//   OPERAND_FMT 1 (bf16 hi + bf16 lo): 16 significant bits, fp32 exponent range;
+//   OPERAND_FMT 0 (fp16 hi + fp16 lo): 22 significant bits -- fp32-class products -- over fp16's range.  hi saturates
+//     at +-65504 (cvt.satfinite) and below 6.1e-5 both planes go subnormal, an ABSOLUTE error <= 3e-8 per element.
+// Every GEMM input on this path is a LayerNorm/ReLU/sigmoid-bounded activation, an O(1) embedding or a weight, so the
+// fp16 range costs nothing and the end-to-end error drops ~8x; gradients in the backward are
+// pre-scaled per call (mdb_bondpred_backward) to sit in that range too.
+constexpr uint32_t OPERAND_FMT = 0;
 __device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t v, float& lo_elem, float& hi_elem) {
+  asm("{\n\t.reg .f16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}"
+      : "=f"(lo_elem), "=f"(hi_elem) : "r"(v));
+}
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-    const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);            // exact: bf16 -> fp32 is a 16-bit shift
-    const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
-    l[i] = pack_f16x2(r0, r1);
+    if constexpr (OPERAND_FMT == 1) {
+      h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+      const float r0 = x[2 * i] - __uint_as_float(h[i] << 16);          // exact: bf16 -> fp32 is a 16-bit shift
+      const float r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+      l[i] = pack_bf16x2(r0, r1);
+    } else {
+      h[i] = pack_f16x2_sat(x[2 * i], x[2 * i + 1]);
+      float h0, h1;
+      unpack_f16x2(h[i], h0, h1);
+      l[i] = pack_f16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
+    }
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);

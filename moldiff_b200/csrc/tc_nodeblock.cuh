@@ -50,8 +50,8 @@ __device__ __forceinline__ void load_half_row(uint32_t taddr, float (&v)[128]) {
   tc::tmem_ld32_wait(r0); tc::tmem_ld32_wait(r1); tc::tmem_ld32_wait(r2); tc::tmem_ld32_wait(r3);
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]);
-    v[64 + i] = __uint_as_float(r2[i]); v[96 + i] = __uint_as_float(r3[i]);
+    v[i] = tc::acc_f(r0[i]); v[32 + i] = tc::acc_f(r1[i]);
+    v[64 + i] = tc::acc_f(r2[i]); v[96 + i] = tc::acc_f(r3[i]);
   }
 }
 

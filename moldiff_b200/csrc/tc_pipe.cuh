@@ -88,9 +88,7 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const
       ++p.n_ready;
       fence_after_sync();
     }
-    constexpr uint32_t id_hh = make_idesc_f16(ROWS, N, 1, 1);   // A hi (bf16) x W hi (bf16)
-    constexpr uint32_t id_lh = make_idesc_f16(ROWS, N, 0, 1);   // A lo (fp16) x W hi (bf16)
-    constexpr uint32_t id_hl = make_idesc_f16(ROWS, N, 1, 0);   // A hi (bf16) x W lo (fp16)
+    constexpr uint32_t idesc = make_idesc_f16(ROWS, N, OPERAND_FMT, OPERAND_FMT);
     constexpr uint32_t SBO_A = (K / 8) * 128;
     const uint32_t d_tmem = p.s->tmem_base + d_col;
     const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
@@ -106,9 +104,9 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const
         const uint64_t da_lo = make_smem_desc(alo + ks * 256, 128, SBO_A);
         const uint64_t db_hi = make_smem_desc(bhi + j * 256, 128, WS::SBO);
         const uint64_t db_lo = make_smem_desc(blo + j * 256, 128, WS::SBO);
-        mma_bf16_ss(d_tmem, da_hi, db_hi, id_hh, (accumulate || ks > 0) ? 1u : 0u);
-        mma_bf16_ss(d_tmem, da_lo, db_hi, id_lh, 1u);
-        mma_bf16_ss(d_tmem, da_hi, db_lo, id_hl, 1u);
+        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+        mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
       }
       mma_commit(&p.s->empty[slot]);
     }

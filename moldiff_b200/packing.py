@@ -253,11 +253,15 @@ def pack_network(sd, *, kind, net_prefix, num_blocks, update_pos, time_dim=0):
 TC_KB = 16   # K columns per weight stage; must equal tc::KB in csrc/tc_pipe.cuh
 
 
+TC_OPERAND_DTYPE = torch.float16      # must match tc::OPERAND_FMT in csrc/tc_engine.cuh (0 = fp16, 1 = bf16)
+TC_ACC_SCALE = 256.0                  # must match tc::ACC_SCALE: images hold 256 x W so that fp16 lo planes stay normal
+
+
 def split_bf16(w):
-    """fp32 -> (hi bf16, lo fp16) with hi + lo ~= w to ~2^-20 relative (round-to-nearest-even both times): bf16 keeps
-    the exponent range, the fp16 remainder (|lo| <= 2^-9 |w|) adds 11 mantissa bits.  Both are 16-bit planes."""
-    hi = w.to(torch.bfloat16)
-    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    """fp32 -> (hi, lo) 16-bit pair, round-to-nearest-even both times.  With fp16 planes hi + lo carries 22 significant
+    bits (|w| < 6e-5 goes subnormal: absolute error <= 3e-8); with bf16 planes 16 bits over fp32's range."""
+    hi = w.to(TC_OPERAND_DTYPE)
+    lo = (w - hi.to(torch.float32)).to(TC_OPERAND_DTYPE)
     return hi, lo
 
 
@@ -273,7 +277,10 @@ def tc_image(w_kn):
     k, n = w_kn.shape
     if k % TC_KB or n % 16:
         raise ValueError(f"tc_image: K={k} must be a multiple of {TC_KB} and N={n} of 16")
-    hi, lo = split_bf16(w_kn.detach().to(torch.float32).cpu().t().contiguous())   # [N][K]
+    w = w_kn.detach().to(torch.float32).cpu().t().contiguous() * TC_ACC_SCALE     # [N][K]
+    if TC_OPERAND_DTYPE == torch.float16:
+        w = w.clamp(-65504.0, 65504.0)              # |weight| > 255 saturates like the kernels' cvt.satfinite
+    hi, lo = split_bf16(w)
     parts = []
     for s in range(k // TC_KB):
         sl = slice(s * TC_KB, (s + 1) * TC_KB)

@@ -183,8 +183,9 @@ def test_packing_roundtrip_and_tc_images(seeded_models):
     assert torch.equal(blob[o:o + 256 * 256].reshape(256, 256), w.t())
     assert all(x % 32 == 0 for row in block_off for x in row if x >= 0)           # 128-byte aligned slots
     img = packing.tc_image(w.t().contiguous())
-    hi, lo = packing.split_bf16(w)                                                 # [N][K] bf16 / fp16
-    assert float((hi.float() + lo.float() - w).abs().max() / w.abs().max()) < 2e-6
+    hi, lo = packing.split_bf16(w * packing.TC_ACC_SCALE)                          # [N][K], images hold 256 x W
+    assert float((hi.double() + lo.double() - w.double() * packing.TC_ACC_SCALE).abs().max()
+                 / (w.abs().max() * packing.TC_ACC_SCALE)) < 3e-7                  # 22 significant bits
     assert img.numel() == 2 * 256 * 256
     # element (n, k) of stage s = k // KB sits at (n%8)*8 + (n//8)*(KB//8)*64 + ((k%KB)//8)*64 + k%8  (int16 units)
     KB = packing.TC_KB
