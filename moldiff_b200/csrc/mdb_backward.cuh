@@ -25,6 +25,22 @@
 // ------------------------------------------------------------------------------------------------
 // edge decoder backward (half-edge tiles, caller order)
 // ------------------------------------------------------------------------------------------------
+// The backward is linear in d_logits, so the whole chain runs on d_logits * 2^k with k chosen per call such that
+// max |d_logits * 2^k| lies in [8, 16): every gradient tile then sits inside the fp16 operand range of the tensor-core
+// GEMMs whatever the caller's objective scale is, and bwd_pos multiplies the result by 2^-k.  Both factors are exact.
+__global__ void grad_amax_kernel(const float* __restrict__ d, size_t n, unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(d[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax_bits, __float_as_uint(m));
+}
+__device__ __forceinline__ int grad_shift(const float* gamax) {      // k: scale 2^k
+  const float m = *gamax;
+  return m > 0.f ? 3 - ilogbf(m) : 0;
+}
+
 struct BwdDecArgs {
   const float* blob;
   HeadOff head;
@@ -32,6 +48,7 @@ struct BwdDecArgs {
   const int *left, *right, *inv;
   int n_half, ke;
   const float* d_logits;   // [Eh][ke]
+  const float* gamax;      // max |d_logits| (grad_amax_kernel)
   float* dh;               // [E][64] sorted order
   float* ddect;            // [N][64] (pre-zeroed)
 };
@@ -57,9 +74,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_decode_kernel(const BwdDecArg
     if (p < a.n_half) { qa = a.inv[p]; qb = a.inv[p + a.n_half]; l = a.left[qa]; r = a.right[qa]; }
     ls[tid] = l; rs[tid] = r; q1[tid] = qa; q2[tid] = qb;
   }
+  const float gscale = scalbnf(1.f, grad_shift(a.gamax));
   for (int i = tid; i < TM * 32; i += NTHREADS) {
     const int r = i >> 5, c = i & 31, p = p0 + r;
-    DL[i] = (p < a.n_half && c < a.ke) ? a.d_logits[(size_t)p * a.ke + c] : 0.f;
+    DL[i] = (p < a.n_half && c < a.ke) ? a.d_logits[(size_t)p * a.ke + c] * gscale : 0.f;
   }
   for (int i = tid; i < TM * C / 4; i += NTHREADS) {
     const int r = i / (C / 4), c4 = i % (C / 4);
@@ -640,7 +658,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_edge_bondffn_kernel(const Bwd
 __global__ void bwd_pos_kernel(int n_edges, const int* __restrict__ left, const int* __restrict__ right,
                                const float* __restrict__ pos, const float* __restrict__ dg,
                                const float* __restrict__ rbf_off, const float* __restrict__ rbf_coeff,
-                               float lo, float hi, float* __restrict__ d_pos) {
+                               float lo, float hi, const float* __restrict__ gamax, float* __restrict__ d_pos) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_edges) return;
   const int l = left[q], r = right[q];
@@ -656,7 +674,7 @@ __global__ void bwd_pos_kernel(int n_edges, const int* __restrict__ left, const 
     const float g = expf(rbf_coeff[k] * (u * u));
     dd = fmaf(dg[(size_t)q * G + k], g * 2.f * rbf_coeff[k] * u, dd);
   }
-  const float s = dd / d;
+  const float s = scalbnf(dd / d, -grad_shift(gamax));
   atomicAdd(d_pos + l * 3 + 0, s * dx); atomicAdd(d_pos + l * 3 + 1, s * dy); atomicAdd(d_pos + l * 3 + 2, s * dz);
   atomicAdd(d_pos + r * 3 + 0, -s * dx); atomicAdd(d_pos + r * 3 + 1, -s * dy); atomicAdd(d_pos + r * 3 + 2, -s * dz);
 }
@@ -708,8 +726,16 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
   CUDA_TRY(cudaMemsetAsync(sv.dg, 0, (size_t)E * G * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(d_pos, 0, (size_t)N * 3 * sizeof(float), st));
 
+  CUDA_TRY(cudaMemsetAsync(sv.gamax, 0, 32 * sizeof(float), st));
+  const size_t n_dl = (size_t)plan->n_half * net->num_edge_types;
+  if (n_dl > 0) {
+    LAUNCH(MDB_K_bwd_decode, st,
+           (grad_amax_kernel<<<(int)std::min<size_t>((n_dl + 255) / 256, 592), 256, 0, st>>>(
+               d_logits, n_dl, reinterpret_cast<unsigned*>(sv.gamax))));
+  }
   BwdDecArgs da;
   memset(&da, 0, sizeof(da));
+  da.gamax = sv.gamax;
   da.blob = net->blob; da.head = head; da.tb = tb; da.left = plan->left; da.right = plan->right; da.inv = plan->inv;
   da.n_half = plan->n_half; da.ke = net->num_edge_types; da.d_logits = d_logits; da.dh = sv.dh; da.ddect = sv.ddect;
   LAUNCH(MDB_K_bwd_decode, st,
@@ -773,7 +799,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
          (bwd_pos_kernel<<<(E + 255) / 256, 256, 0, st>>>(E, plan->left, plan->right, pos, sv.dg,
                                                          net->blob + net->head_off[MDB_H_RBF_OFFSET],
                                                          net->blob + net->head_off[MDB_H_RBF_COEFF],
-                                                         net->rbf_start, net->rbf_stop, d_pos)));
+                                                         net->rbf_start, net->rbf_stop, sv.gamax, d_pos)));
   CUDA_TRY(cudaGetLastError());
   return MDB_OK;
 }

@@ -738,6 +738,7 @@ struct Saved {
   float *dnl;                // [2][N][128]
   float *dgn;                // [2][N][32]
   float *ddect;              // [N][64]
+  float *gamax;              // [32]: word 0 = bit pattern of max |d_logits| of the current backward call
 };
 
 constexpr int TAB_FLOATS = 3 * D + 2 * 128 + 2 * 32 + 2 * C;   // per node
@@ -762,6 +763,7 @@ size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   sv.dul = take(N * C); sv.dur = take(N * C);
   sv.dagg = take(N * D); sv.dgx = take(N * D); sv.dhn = take(N * D);
   sv.dnl = take(2 * N * 128); sv.dgn = take(2 * N * 32); sv.ddect = take(N * C);
+  sv.gamax = take(32);
   return o;
 }
 
