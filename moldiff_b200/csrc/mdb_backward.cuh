@@ -773,10 +773,10 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
-      ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de;
+      ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
       fill_nb_vecs(ta.v, net->blob_host, ea.off);
       LAUNCH(MDB_K_tc_nodeblock_bwd, st,
-             (tc_nodeblock_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB_BWD, st>>>(ta)));
+             (tc_nodeblock_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, tc::RB_THREADS, SMEM_TC_NB_BWD, st>>>(ta)));
     } else {
       LAUNCH(MDB_K_bwd_edge_nodeblock, st, (bwd_edge_nodeblock_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_NB, st>>>(ea)));
     }

@@ -5,7 +5,7 @@
 // the columns of the same rows), lane 0 of the next warp streams weight stages L2 -> smem with cp.async.bulk,
 // lane 0 of the last warp issues tcgen05.mma.  All three roles walk the same static sequence of GEMMs; they meet only on
 // mbarriers:
-//     a_ready (128 arrivals)  rows -> MMA   "A planes written, previous accumulator drained"
+//     a_ready[g] (one arrival per row warp)  rows -> MMA   "A planes (K-slice g) written, previous accumulator drained"
 //     full[s] / empty[s]      producer <-> MMA, one weight stage each (empty is signalled by tcgen05.commit)
 //     done                    MMA -> rows   "accumulator complete"
 // The producer runs ahead across GEMM boundaries, so weight fetch overlaps the row threads' epilogues.
@@ -20,9 +20,10 @@ constexpr int KB = 16;                 // K columns per weight stage
 constexpr int NSTAGE = 4;
 constexpr uint32_t STAGE_SLOT = 256 * KB * 2 * 2;   // bytes reserved per stage (N = 256 worst case): 32 KB
 
+constexpr int NGRP = 4;                // a_ready groups: the A planes of a K = 256 GEMM can be published in 4 K-slices
 template <int NS>
 struct PipeSmemT {                     // lives in shared memory
-  uint64_t full[NS], empty[NS], done, a_ready;
+  uint64_t full[NS], empty[NS], done, a_ready[NGRP];
   uint32_t tmem_base;
 };
 using PipeSmem = PipeSmemT<NSTAGE>;
@@ -35,28 +36,61 @@ struct PipeT {
   uint32_t n_done;      // GEMMs completed (MMA thread / row threads)
   uint32_t n_ready;     // a_ready phases consumed (MMA thread)
   int role;             // 0 = row thread, 1 = producer thread, 2 = MMA thread, 3 = idle lane
+  long long* dbg;       // optional clock64 stamps of the MMA thread (phase-timing tool), else nullptr
 };
 using Pipe = PipeT<NSTAGE>;
 
 template <int NRW = 4, int NS = NSTAGE>   // NRW row warps: 4 = one thread per row, 8 / 16 = two / four threads per row
 __device__ __forceinline__ void pipe_init(PipeT<NS>& p, PipeSmemT<NS>* s, uint8_t* stages) {
-  p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0;
+  p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0; p.dbg = nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   p.role = warp < NRW ? 0 : (lane == 0 ? (warp == NRW ? 1 : 2) : 3);
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&s->full[i], 1); mbar_init(&s->empty[i], 1); }
     mbar_init(&s->done, 1);
-    mbar_init(&s->a_ready, NRW * 32);
+    for (int g = 0; g < NGRP; ++g) mbar_init(&s->a_ready[g], NRW);   // one elected arrival per row warp
     fence_barrier_init();
   }
+}
+
+// Register rebalancing between warp roles (setmaxnreg, whole warpgroups): kernels launched with RB_THREADS = 384 threads
+// (8 row warps = warpgroups 0-1; producer warp, MMA warp and two idle warps = warpgroup 2) compile to 168 registers per
+// thread; warpgroup 2 shrinks to 40 and the row warpgroups grow to 232, which removes the epilogue spills.
+constexpr int RB_THREADS = 384;
+template <int NREG> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
+template <int NREG> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
+// CTA-wide barrier usable from role-specialised code paths (the two sides reach it from different program points)
+__device__ __forceinline__ void cta_sync() { asm volatile("barrier.sync 0;" ::: "memory"); }
+
+// pipe_init for role-specialised kernel bodies: IS_ROW is a compile-time constant, so each instantiation only keeps its own
+// side of every `if (p.role == ...)`.
+template <int NRW, bool IS_ROW, int NS>
+__device__ __forceinline__ void pipe_init_split(PipeT<NS>& p, PipeSmemT<NS>* s, uint8_t* stages) {
+  pipe_init<NRW, NS>(p, s, stages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if constexpr (IS_ROW) p.role = 0;
+  else p.role = lane == 0 ? (warp == NRW ? 1 : (warp == NRW + 1 ? 2 : 3)) : 3;
 }
 
 // Row threads: "my part of the A planes is written and I no longer read the accumulator".
 template <int NS>
 __device__ __forceinline__ void rows_publish(PipeT<NS>& p) {
-  fence_proxy_async();
+  fence_proxy_async();       // every lane: its own smem writes -> async proxy
   fence_before_sync();
-  mbar_arrive(&p.s->a_ready);
+  __syncwarp();              // ... then one arrival per warp instead of 32 serialised ones on the same barrier word
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int g = 0; g < NGRP; ++g) mbar_arrive(&p.s->a_ready[g]);
+  }
+}
+// Sliced publication (pairs with gemm<..., NPARTS> below): "my columns of K-slice g are written".  Slice 0 also says
+// "I no longer read the accumulator" (every row thread drains its accumulator part into registers before it stores).
+template <int NS>
+__device__ __forceinline__ void rows_publish_group(PipeT<NS>& p, int g) {
+  fence_proxy_async();
+  if (g == 0) fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&p.s->a_ready[g]);
 }
 // Row threads: wait for the accumulator of the next GEMM in program order.
 template <int NS>
@@ -66,51 +100,101 @@ __device__ __forceinline__ void rows_wait_acc(PipeT<NS>& p) {
   fence_after_sync();
 }
 
+// Row thread owning NC = 256 / NPARTS columns [k0, k0 + NC) of row r of the K = 256 A planes: value i of its part is f(i);
+// convert, store and publish them in NGRP column groups (sliced protocol, see gemm<..., NPARTS>).
+template <int NC, int NSLOT, typename F>
+__device__ __forceinline__ void store_a_sliced(PipeT<NSLOT>& p, uint8_t* a_hi, uint8_t* a_lo, int r, int k0, F&& f) {
+  constexpr int CPG = NC / 8 / NGRP;   // 16-byte chunks per group
+  static_assert(CPG >= 1 && CPG * 8 * NGRP == NC, "part width must split into NGRP groups of whole chunks");
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) {
+#pragma unroll
+    for (int c = g * CPG; c < (g + 1) * CPG; ++c) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = f(c * 8 + i);
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      const uint32_t off = a_chunk_off<256>(r, k0 / 8 + c);
+      *reinterpret_cast<uint4*>(a_hi + off) = hi;
+      *reinterpret_cast<uint4*>(a_lo + off) = lo;
+    }
+    rows_publish_group(p, g);
+  }
+}
+
 // One GEMM: D[tmem col d_col .. +N) (+)= A(a_hi, a_lo planes, K columns) * W (image at w_img).
 // Called by ALL threads of the CTA at the same program point; row threads return immediately.
 // wait_ready = false chains a second GEMM onto the same A planes / accumulator epoch without a new a_ready phase.
-template <int K, int N, int NSLOT>
+//
+// NPARTS > 0 selects the SLICED protocol: the A planes are written by NPARTS threads per row (part p owns columns
+// [p K / NPARTS, (p + 1) K / NPARTS)), each in NGRP column groups published with rows_publish_group(g).  K-slice g of the
+// GEMM is group g of every part, so the MMAs of slice g are issued -- and its weight stages consumed -- while the row
+// threads are still converting and storing slices g+1.. : the K loop runs in the permuted order kstep(s) on both the
+// producer and the MMA side.
+template <int NS, int NPARTS>
+__device__ __forceinline__ int kstep_of(int s) {
+  if constexpr (NPARTS == 0) {
+    return s;
+  } else {
+    constexpr int SPG = NS / NGRP;          // K stages per slice
+    constexpr int SPP = SPG / NPARTS;       // ... of which per part
+    static_assert(SPP >= 1 && SPP * NPARTS * NGRP == NS, "slice layout");
+    return ((s % SPG) / SPP) * (NS / NPARTS) + (s / SPG) * SPP + (s % SPP);
+  }
+}
+template <int K, int N, int NSLOT, int NPARTS = 0>
 __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_img,
                                      uint32_t d_col, bool accumulate, bool wait_ready, bool signal_done) {
   using WS = WStage<N, KB>;
   constexpr int NS = K / KB;
   static_assert(K % KB == 0, "K must be a multiple of the stage depth");
+  static_assert(KB == 16, "one UMMA K step per weight stage");
   if (p.role == 1) {
     for (int s = 0; s < NS; ++s, ++p.it) {
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->empty[slot], ph ^ 1);
       mbar_arrive_expect_tx(&p.s->full[slot], WS::STAGE_BYTES);
-      bulk_g2s(p.stages + slot * STAGE_SLOT, w_img + (size_t)s * WS::STAGE_BYTES, WS::STAGE_BYTES, &p.s->full[slot]);
+      bulk_g2s(p.stages + slot * STAGE_SLOT, w_img + (size_t)kstep_of<NS, NPARTS>(s) * WS::STAGE_BYTES, WS::STAGE_BYTES,
+               &p.s->full[slot]);
     }
   } else if (p.role == 2) {
+    const uint32_t ready_parity = p.n_ready & 1;
     if (wait_ready) {
-      mbar_wait(&p.s->a_ready, p.n_ready & 1);
       ++p.n_ready;
-      fence_after_sync();
+      if constexpr (NPARTS == 0) {
+        mbar_wait(&p.s->a_ready[NGRP - 1], ready_parity);   // groups are published in order: the last implies all
+        fence_after_sync();
+      }
     }
     constexpr uint32_t idesc = make_idesc_f16(ROWS, N, OPERAND_FMT, OPERAND_FMT);
     constexpr uint32_t SBO_A = (K / 8) * 128;
     const uint32_t d_tmem = p.s->tmem_base + d_col;
     const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
     for (int s = 0; s < NS; ++s, ++p.it) {
+      if constexpr (NPARTS != 0) {
+        if (wait_ready && s % (NS / NGRP) == 0) {
+          mbar_wait(&p.s->a_ready[s / (NS / NGRP)], ready_parity);
+          fence_after_sync();
+          if (p.dbg) p.dbg[16 + s / (NS / NGRP)] = clock64();
+        }
+      }
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->full[slot], ph);
       fence_after_sync();
       const uint32_t bhi = smem_u32(p.stages + slot * STAGE_SLOT), blo = bhi + WS::PLANE_BYTES;
-#pragma unroll
-      for (int j = 0; j < KB / 16; ++j) {
-        const uint32_t ks = s * (KB / 16) + j;
-        const uint64_t da_hi = make_smem_desc(ahi + ks * 256, 128, SBO_A);
-        const uint64_t da_lo = make_smem_desc(alo + ks * 256, 128, SBO_A);
-        const uint64_t db_hi = make_smem_desc(bhi + j * 256, 128, WS::SBO);
-        const uint64_t db_lo = make_smem_desc(blo + j * 256, 128, WS::SBO);
-        mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (accumulate || ks > 0) ? 1u : 0u);
-        mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-        mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
-      }
+      const uint32_t ks = (uint32_t)kstep_of<NS, NPARTS>(s);
+      const uint64_t da_hi = make_smem_desc(ahi + ks * 256, 128, SBO_A);
+      const uint64_t da_lo = make_smem_desc(alo + ks * 256, 128, SBO_A);
+      const uint64_t db_hi = make_smem_desc(bhi, 128, WS::SBO);
+      const uint64_t db_lo = make_smem_desc(blo, 128, WS::SBO);
+      mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
+      mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
+      mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
       mma_commit(&p.s->empty[slot]);
     }
     if (signal_done) mma_commit(&p.s->done);
+    if (p.dbg) p.dbg[20] = clock64();
   }
 }
 

@@ -38,3 +38,8 @@ for i, n in enumerate(names):
     print(f"  {n:32s} {d[:, i].mean():9.0f} {np.median(d[:, i]):9.0f} {np.percentile(d[:, i], 90):9.0f}")
 tot = t[:, 15] - t[:, 0]
 print(f"  {'total':32s} {tot.mean():9.0f} {np.median(tot):9.0f} {np.percentile(tot, 90):9.0f}")
+
+# MMA-thread stamps of the LAST sliced GEMM (G5): a_ready group waits and the final commit, relative to the start of epilogue 3
+rel = lambda c: (t[:, c] - t[:, 4])
+print("G5 (sliced): rows start epi3 = 0; rows end epi3 %.0f; MMA saw group 0/1/2/3 at %.0f / %.0f / %.0f / %.0f; MMA issued last commit %.0f; rows saw done %.0f"
+      % (rel(9).mean(), rel(16).mean(), rel(17).mean(), rel(18).mean(), rel(19).mean(), rel(20).mean(), rel(5).mean()))
