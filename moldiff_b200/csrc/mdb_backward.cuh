@@ -697,6 +697,7 @@ int ensure_bwd_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(bwd_edge_nodeblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_NB));
   CUDA_TRY(cudaFuncSetAttribute(bwd_edge_bondffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_FFN));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD));
+  CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD16));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD));
   done = true;
   return MDB_OK;
@@ -768,15 +769,28 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     ea.e = sv.e + (size_t)i * EC; ea.sl = sv.slsr + (size_t)i * 2 * NC; ea.fl = tbi.fl; ea.fr = tbi.fr;
     LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
     if (net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_NB_G2] >= 0) {
-      TcNbBwdArgs ta;
-      memset(&ta, 0, sizeof(ta));
-      ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
-      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
-      ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
-      ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
-      fill_nb_vecs(ta.v, net->blob_host, ea.off);
-      LAUNCH(MDB_K_tc_nodeblock_bwd, st,
-             (tc_nodeblock_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, tc::RB_THREADS, SMEM_TC_NB_BWD, st>>>(ta)));
+      static const bool bwd16 = []() { const char* e = getenv("MDB_TC_NB_BWD16"); return e == nullptr || e[0] != '0'; }();
+      if (bwd16) {
+        TcNbBwd16Args ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
+        for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
+        ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
+        ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
+        ta.scr_he = sv.scr_he; ta.scr_dm = reinterpret_cast<uint8_t*>(sv.scr_dm);
+        LAUNCH(MDB_K_tc_nodeblock_bwd, st,
+               (tc_nodeblock_bwd16_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, NB16_THREADS, SMEM_TC_NB_BWD16, st>>>(ta)));
+      } else {
+        TcNbBwdArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
+        for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
+        ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
+        ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
+        fill_nb_vecs(ta.v, net->blob_host, ea.off);
+        LAUNCH(MDB_K_tc_nodeblock_bwd, st,
+               (tc_nodeblock_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, tc::RB_THREADS, SMEM_TC_NB_BWD, st>>>(ta)));
+      }
     } else {
       LAUNCH(MDB_K_bwd_edge_nodeblock, st, (bwd_edge_nodeblock_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_NB, st>>>(ea)));
     }

@@ -667,6 +667,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_bondffn.cuh"
 #include "tc_edge_d.cuh"
 #include "tc_nodeblock16.cuh"
+#include "tc_nodeblock_bwd16.cuh"
 #include "tc_node.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -739,6 +740,7 @@ struct Saved {
   float *dgn;                // [2][N][32]
   float *ddect;              // [N][64]
   float *gamax;              // [32]: word 0 = bit pattern of max |d_logits| of the current backward call
+  float *scr_he, *scr_dm;    // [ceil(E/128)*128][256] each: tc_nodeblock_bwd16 scratch slabs (he fp32 / d msg operand planes)
 };
 
 constexpr int TAB_FLOATS = 3 * D + 2 * 128 + 2 * 32 + 2 * C;   // per node
@@ -764,6 +766,8 @@ size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   sv.dagg = take(N * D); sv.dgx = take(N * D); sv.dhn = take(N * D);
   sv.dnl = take(2 * N * 128); sv.dgn = take(2 * N * 32); sv.ddect = take(N * C);
   sv.gamax = take(32);
+  const int64_t e_pad = (E + 127) / 128 * 128;
+  sv.scr_he = take(e_pad * D); sv.scr_dm = take(e_pad * D);
   return o;
 }
 

@@ -1,7 +1,14 @@
-// 16-row-warp variant of tc_nodeblock_fwd_kernel: four threads per tile row (64 columns each) instead of two.
-// The row epilogues of the 8-warp kernel are issue/latency bound (IPC ~1 per SM); doubling the resident row
-// warps (4 per scheduler) is the cheapest way to overlap their dependent instruction chains.  Same math, same
-// pipeline protocol; LayerNorm statistics are merged exactly over the four parts of a row.
+// tc_nodeblock_fwd16_kernel: the NodeBlock per-edge path (reference models/graph.py:42-50) on tcgen05 with 16 row warps
+// (four threads per tile row, 64 columns each) and ROLLED epilogues.
+//
+// Why rolled: the fully unrolled register-resident epilogues (tc_nodeblock_fwd_kernel) are 100-270 KB of straight-line
+// SASS that every tile executes exactly once -- ncu's source view showed 50-60 % of their issue slots stalled on
+// instruction fetch (no_inst).  Here an epilogue is one or two `#pragma unroll 1` loops over 16-column chunks that re-read
+// the accumulator from TMEM (cheap) instead of holding 64-128 values in registers: the hot code fits the instruction
+// cache, needs < 100 registers, and chunk c of an epilogue is K-slice c of the next GEMM (sliced publication, tc_pipe.cuh).
+//
+// TMEM: two 256-column accumulators A0 / A1.  An epilogue that re-reads its accumulator while it publishes slices must not
+// feed a GEMM that overwrites the same accumulator:  G1 -> A1, G2 -> A0, G3 (msg) -> A1, G4 -> A0, G5 -> A0 (unsliced).
 //
 // Included by mdb_forward.cu inside its anonymous namespace (after tc_bondffn.cuh).
 #pragma once
@@ -17,39 +24,47 @@ static_assert(NB16_VEC_OFF % 16 == 0, "vector block must be 16-byte aligned");
 using Pipe16 = tc::PipeT<NB16_NS>;
 using PipeSmem16 = tc::PipeSmemT<NB16_NS>;
 
-// LayerNorm statistics of a 256-wide row held as 4 x 64 columns by four threads: returns (mean, rstd)
-__device__ __forceinline__ float2 ln_stats_quarter(const float (&v)[64], float2* stat, int row, int part) {
+// running (count, mean, M2) of a row part, merged chunk by chunk (Chan et al.: exact, no cancellation)
+struct RunStat { float n, mean, m2; };
+__device__ __forceinline__ void stat_add16(RunStat& s, const float (&x)[16]) {
   float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 64; i += 4) { s4[0] += v[i]; s4[1] += v[i + 1]; s4[2] += v[i + 2]; s4[3] += v[i + 3]; }
-  const float m_p = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 64.f);
+  for (int i = 0; i < 16; i += 4) { s4[0] += x[i]; s4[1] += x[i + 1]; s4[2] += x[i + 2]; s4[3] += x[i + 3]; }
+  const float mc = ((s4[0] + s4[1]) + (s4[2] + s4[3])) * (1.f / 16.f);
   float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 64; i += 4) {
+  for (int i = 0; i < 16; i += 4) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const float d = v[i + u] - m_p; q4[u] = fmaf(d, d, q4[u]); }
+    for (int u = 0; u < 4; ++u) { const float d = x[i + u] - mc; q4[u] = fmaf(d, d, q4[u]); }
   }
-  stat[part * tc::ROWS + row] = make_float2(m_p, (q4[0] + q4[1]) + (q4[2] + q4[3]));
+  const float nt = s.n + 16.f, delta = mc - s.mean, w = 16.f / nt;
+  s.mean = fmaf(delta, w, s.mean);
+  s.m2 += (q4[0] + q4[1]) + (q4[2] + q4[3]) + delta * delta * s.n * w;
+  s.n = nt;
+}
+// merge the four 64-column parts of a row (equal counts): returns (mean, rstd) of the 256-wide row
+__device__ __forceinline__ float2 ln_merge_quarter(float m_p, float q_p, float2* stat, int row, int part) {
+  stat[part * tc::ROWS + row] = make_float2(m_p, q_p);
   asm volatile("bar.sync 1, 512;" ::: "memory");
   const float2 s0 = stat[row], s1 = stat[tc::ROWS + row], s2 = stat[2 * tc::ROWS + row], s3 = stat[3 * tc::ROWS + row];
   asm volatile("bar.sync 1, 512;" ::: "memory");
   const float mean = 0.25f * ((s0.x + s1.x) + (s2.x + s3.x));
   const float d0 = s0.x - mean, d1 = s1.x - mean, d2 = s2.x - mean, d3 = s3.x - mean;
-  const float m2 = (s0.y + s1.y) + (s2.y + s3.y) + 64.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));   // exact merge
+  const float m2 = (s0.y + s1.y) + (s2.y + s3.y) + 64.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
   return make_float2(mean, 1.f / sqrtf(m2 * (1.f / 256.f) + LN_EPS));
 }
-
-// v[i] = f(acc[i], v[i]) for this thread's 64 accumulator columns, read from TMEM in two 32-column chunks: v[] already
-// holds the gathered operand (loaded BEFORE the accumulator wait), so the peak register footprint is 64 + 32.
-template <typename F>
-__device__ __forceinline__ void combine_cols64(uint32_t taddr, float (&v)[64], F&& f) {
+// 16 values of row r, columns [k0, k0 + 16) -> the K = 256 A planes (two 16-byte chunks per plane)
+__device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int r, int k0, const float (&v)[16]) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    tc::tmem_ld32_issue(taddr + c * 32, r);
-    tc::tmem_ld32_wait(r);
+    float x[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[c * 32 + i] = f(c * 32 + i, tc::acc_f(r[i]), v[c * 32 + i]);
+    for (int i = 0; i < 8; ++i) x[i] = v[c * 8 + i];
+    uint4 hi, lo;
+    tc::split8(x, hi, lo);
+    const uint32_t off = tc::a_chunk_off<256>(r, k0 / 8 + c);
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
   }
 }
 
@@ -64,10 +79,12 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   PipeSmem16* ps = reinterpret_cast<PipeSmem16*>(stages + NB16_NS * tc::STAGE_SLOT);
   float2* stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ps) + 128);     // [4][128]
   int* ls = reinterpret_cast<int*>(stat + 4 * tc::ROWS);
-  // per-column parameter vectors, copied once from the kernel arguments: register-indexed constant-bank loads (LDC, two
-  // values per instruction) were the epilogues' throughput limiter; warp-uniform LDS.128 reads broadcast four per instruction
+  // Per-column parameter vectors in shared memory (copied from the fp32 blob with one coalesced 16-byte load per row
+  // thread): the epilogues read them with warp-uniform LDS.128 -- four values per instruction.  Register-indexed
+  // constant-bank loads (LDC, one or two values each) made the rolled LayerNorm epilogue MIO-bound (ncu: 46 % of its
+  // samples on LDC).
   float* vecs = reinterpret_cast<float*>(smem_raw + NB16_VEC_OFF);
-  const float* v_en1_b = vecs, *v_en1_g = vecs + D, *v_en1_be = vecs + 2 * D, *v_en2_b = vecs + 3 * D, *v_msg_b = vecs + 4 * D,
+  const float *v_en1_b = vecs, *v_en1_g = vecs + D, *v_en1_be = vecs + 2 * D, *v_en2_b = vecs + 3 * D, *v_msg_b = vecs + 4 * D,
               *v_g1_g = vecs + 5 * D, *v_g1_be = vecs + 6 * D, *v_g2_b = vecs + 7 * D;
   float* out_tile = reinterpret_cast<float*>(smem_raw);
 
@@ -94,16 +111,22 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
     }
     if (q < a.n_edges) { my_r = a.right[q]; if (part == 0) ls[row] = a.left[q]; }
     else if (part == 0) ls[row] = -1;
-    static_assert(sizeof(NbVecs) == 8 * D * sizeof(float), "NbVecs layout");
-    const float* src = reinterpret_cast<const float*>(&a.v);
-#pragma unroll
-    for (int i = 0; i < 8 * D / (NB16_NRW * 32); ++i) vecs[i * NB16_NRW * 32 + tid] = src[i * NB16_NRW * 32 + tid];
+    const int vj = tid >> 6;                    // 64 threads per vector
+    int so = a.off.o[MDB_S_NB_EN1_B];
+    if (vj == 1) so = a.off.o[MDB_S_NB_EN1_G];
+    if (vj == 2) so = a.off.o[MDB_S_NB_EN1_BE];
+    if (vj == 3) so = a.off.o[MDB_S_NB_EN2_B];
+    if (vj == 4) so = a.off.o[MDB_S_NB_MSG_B];
+    if (vj == 5) so = a.off.o[MDB_S_NB_G1_G];
+    if (vj == 6) so = a.off.o[MDB_S_NB_G1_BE];
+    if (vj == 7) so = a.off.o[MDB_S_NB_G2_B];
+    *reinterpret_cast<float4*>(vecs + tid * 4) = *reinterpret_cast<const float4*>(a.blob + so + (tid & 63) * 4);
   }
   tc::fence_before_sync();
   tc::cta_sync();
   tc::fence_after_sync();
   const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t D0 = 0, D1 = 256;
+  const uint32_t A0 = lane_base + pc, A1 = lane_base + 256 + pc;     // this thread's part of the two accumulators
   const int rr = my_r < 0 ? 0 : my_r;
   TC_STAMP(1);
 
@@ -112,73 +135,117 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
     tc::rows_publish(p);
     TC_STAMP(6);
   }
-  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), D1, false, true, true);
+  // G1: edge_net.net.0 -> A1                                                      graph.py:42
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_EN1), 256, false, true, true);
   if (IS_ROW) {
     tc::rows_wait_acc(p);
     TC_STAMP(2);
-    float v[64];
-    load_cols_tm<64>(lane_base + D1 + pc, v);
+    RunStat rs = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float x[16];
+      tc::tmem_ld16(A1 + c * 16, x);
 #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] += v_en1_b[pc + i];
-    const float2 ms = ln_stats_quarter(v, stat, row, part);
-    const float* gam = v_en1_g + pc;
-    const float* bet = v_en1_be + pc;
-    tc::store_a_sliced<64>(p, x_hi, x_lo, row, pc,
-                           [&](int i) { return fmaxf((v[i] - ms.x) * ms.y * gam[i] + bet[i], 0.f); });
+      for (int i = 0; i < 16; ++i) x[i] += v_en1_b[pc + c * 16 + i];
+      stat_add16(rs, x);
+    }
+    const float2 ms = ln_merge_quarter(rs.mean, rs.m2, stat, row, part);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float x[16];
+      tc::tmem_ld16(A1 + c * 16, x);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = pc + c * 16 + i;
+        x[i] = fmaxf((x[i] + v_en1_b[k] - ms.x) * ms.y * v_en1_g[k] + v_en1_be[k], 0.f);
+      }
+      store_a16(x_hi, x_lo, row, pc + c * 16, x);
+      tc::rows_publish_group(p, c);
+    }
     TC_STAMP(7);
   }
-  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_EN2), D1, false, true, true);
+  // G2: edge_net.net.3 -> A0 ; m = he * node_net(x)[col]                           graph.py:43
+  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_EN2), 0, false, true, true);
   if (IS_ROW) {
     const float* hn = tb.hn + (size_t)rr * D + pc;
-    float v[64];                                 // gathered node_net(x)[col] row part: requested BEFORE the accumulator wait
+    float hv[64];                                // gathered node_net(x)[col] row part: requested BEFORE the accumulator wait
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
       const float4 t4 = *reinterpret_cast<const float4*>(hn + i);
-      v[i] = t4.x; v[i + 1] = t4.y; v[i + 2] = t4.z; v[i + 3] = t4.w;
+      hv[i] = t4.x; hv[i + 1] = t4.y; hv[i + 2] = t4.z; hv[i + 3] = t4.w;
     }
     tc::rows_wait_acc(p);
     TC_STAMP(3);
-    const float* b2 = v_en2_b + pc;
-    combine_cols64(lane_base + D1 + pc, v, [&](int i, float acc, float h) { return (acc + b2[i]) * h; });
-    tc::store_a_sliced<64>(p, x_hi, x_lo, row, pc, [&](int i) { return v[i]; });
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                // unrolled: hv[] must stay in registers
+      float x[16];
+      tc::tmem_ld16(A0 + c * 16, x);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = (x[i] + v_en2_b[pc + c * 16 + i]) * hv[c * 16 + i];
+      store_a16(x_hi, x_lo, row, pc + c * 16, x);
+      tc::rows_publish_group(p, c);
+    }
     TC_STAMP(8);
   }
-  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_MSG), D0, false, true, false);
-  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), D1, false, false, true);
+  // G3: msg_net -> A1 (stays in TMEM) ; G4: gate.net.0 edge columns -> A0          graph.py:43,46
+  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_MSG), 256, false, true, false);
+  tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), 0, false, false, true);
   if (IS_ROW) {
     const float* gxr = tb.gx + (size_t)rr * D + pc;
-    float v[64];                                 // hoisted node / time / bias part of gate.net.0, gathered before the wait
+    float gv[64];                                // hoisted node / time / bias part of gate.net.0, gathered before the wait
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
       const float4 t4 = *reinterpret_cast<const float4*>(gxr + i);
-      v[i] = t4.x; v[i + 1] = t4.y; v[i + 2] = t4.z; v[i + 3] = t4.w;
+      gv[i] = t4.x; gv[i + 1] = t4.y; gv[i + 2] = t4.z; gv[i + 3] = t4.w;
     }
     tc::rows_wait_acc(p);
     TC_STAMP(4);
-    combine_cols64(lane_base + D1 + pc, v, [&](int, float acc, float g) { return acc + g; });
-    const float2 ms = ln_stats_quarter(v, stat, row, part);
-    const float* gam = v_g1_g + pc;
-    const float* bet = v_g1_be + pc;
-    tc::store_a_sliced<64>(p, x_hi, x_lo, row, pc,
-                           [&](int i) { return fmaxf((v[i] - ms.x) * ms.y * gam[i] + bet[i], 0.f); });
+    RunStat rs = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                // unrolled (gv[] in registers): fold the gathered row into the accumulator
+      float x[16];
+      tc::tmem_ld16(A0 + c * 16, x);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] += gv[c * 16 + i];
+      tc::tmem_st16(A0 + c * 16, x);
+      stat_add16(rs, x);
+    }
+    tc::tmem_st_wait();
+    const float2 ms = ln_merge_quarter(rs.mean, rs.m2, stat, row, part);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float x[16];
+      tc::tmem_ld16(A0 + c * 16, x);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = pc + c * 16 + i;
+        x[i] = fmaxf((x[i] - ms.x) * ms.y * v_g1_g[k] + v_g1_be[k], 0.f);
+      }
+      store_a16(x_hi, x_lo, row, pc + c * 16, x);
+    }
+    tc::rows_publish(p);                         // unsliced: G5 overwrites the accumulator this epilogue re-reads
     TC_STAMP(9);
   }
-  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_G2), D1, false, true, true);
+  // G5: gate.net.3 -> A0                                                          graph.py:46
+  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_G2), 0, false, true, true);
   if (IS_ROW) {
     tc::rows_wait_acc(p);
     TC_STAMP(5);
-    {
-      float g[64], m[64];
-      load_cols_tm<64>(lane_base + D1 + pc, g);
-      load_cols_tm<64>(lane_base + D0 + pc, m);
+    // out = (msg + b) * sigmoid(gate + b)  -> smem tile (all operand planes are dead now)     graph.py:47
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float g[16], m[16];
+      tc::tmem_ld16(A0 + c * 16, g);
+      tc::tmem_ld16(A1 + c * 16, m);
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) {
+      for (int i = 0; i < 16; i += 4) {
+        const int k = pc + c * 16 + i;
         float4 o;
-        o.x = (m[i] + v_msg_b[pc + i]) * tc::fast_sigmoid(g[i] + v_g2_b[pc + i]);
-        o.y = (m[i + 1] + v_msg_b[pc + i + 1]) * tc::fast_sigmoid(g[i + 1] + v_g2_b[pc + i + 1]);
-        o.z = (m[i + 2] + v_msg_b[pc + i + 2]) * tc::fast_sigmoid(g[i + 2] + v_g2_b[pc + i + 2]);
-        o.w = (m[i + 3] + v_msg_b[pc + i + 3]) * tc::fast_sigmoid(g[i + 3] + v_g2_b[pc + i + 3]);
-        *reinterpret_cast<float4*>(out_tile + row * OUT_LD + pc + i) = o;
+        o.x = (m[i] + v_msg_b[k]) * tc::fast_sigmoid(g[i] + v_g2_b[k]);
+        o.y = (m[i + 1] + v_msg_b[k + 1]) * tc::fast_sigmoid(g[i + 1] + v_g2_b[k + 1]);
+        o.z = (m[i + 2] + v_msg_b[k + 2]) * tc::fast_sigmoid(g[i + 2] + v_g2_b[k + 2]);
+        o.w = (m[i + 3] + v_msg_b[k + 3]) * tc::fast_sigmoid(g[i + 3] + v_g2_b[k + 3]);
+        *reinterpret_cast<float4*>(out_tile + row * OUT_LD + k) = o;
       }
     }
     tc::fence_before_sync();
