@@ -144,6 +144,7 @@ struct BwdNodeArgs {
   const float* xA;       // saved h_node entering block i-1    (phase A: table recompute)
   const float* aggA;     // saved aggregated messages of block i-1
   float *flA, *frA;      // table destinations for phase A
+  int red_blocked;       // dgx / dhn are in the node-blocked layout (written by tc_nodeblock_bwd16_kernel)
 };
 
 // load a [64][W] tile of a per-node table into smem (zero padded rows)
@@ -156,6 +157,18 @@ __device__ __forceinline__ void load_node_tile(float* dst, const float* __restri
     if (n < n_nodes) v = reinterpret_cast<const float4*>(src + (size_t)n * W)[c4];
     reinterpret_cast<float4*>(dst + r * W)[c4] = v;
   }
+}
+
+// same for a node-blocked [.][256] table (tile_engine.cuh: blk_off); rows beyond n_nodes hold zeros there
+__device__ __forceinline__ void load_node_tile_blocked(float* dst, const float* __restrict__ src, int row0) {
+  for (int i = threadIdx.x; i < TM * D / 4; i += NTHREADS) {
+    const int r = i & (TM - 1), c4 = i / TM;          // consecutive threads -> consecutive nodes: contiguous 16-byte pieces
+    reinterpret_cast<float4*>(dst + r * D)[c4] = *reinterpret_cast<const float4*>(src + blk_off(row0 + r, c4));
+  }
+}
+__device__ __forceinline__ void zero_node_rows_blocked(float* __restrict__ dst, int row0) {   // TM = 64 nodes = 2 whole blocks
+  for (int i = threadIdx.x; i < TM * D / 4; i += NTHREADS)
+    reinterpret_cast<float4*>(dst + (size_t)row0 * D)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 template <int W>
@@ -213,11 +226,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_node_kernel(const BwdNodeArgs
     tile_gemm<32, D, true>(dx, A, 32, W_(T_EL_GN), Ws);               // bond_ffn gate.net.0 node columns
     load_node_tile<32>(A, sv.dgn + (size_t)a.n_nodes * 32, row0, a.n_nodes);  __syncthreads();
     tile_gemm<32, D, true>(dx, A, 32, W_(T_ER_GN), Ws);
-    load_node_tile<D>(A, sv.dgx, row0, a.n_nodes);  __syncthreads();
+    if (a.red_blocked) load_node_tile_blocked(A, sv.dgx, row0); else load_node_tile<D>(A, sv.dgx, row0, a.n_nodes);
+    __syncthreads();
     tile_gemm<D, D, true>(dx, A, D, W_(T_NB_GX), Ws);                 // NodeBlock gate.net.0 node columns
     // node_net backward: hn = W2 relu(LN(W1 x + b1)) + b2                        graph.py:39
     load_node_tile<D>(X, a.xB, row0, a.n_nodes);
-    load_node_tile<D>(A, sv.dhn, row0, a.n_nodes);
+    if (a.red_blocked) load_node_tile_blocked(A, sv.dhn, row0); else load_node_tile<D>(A, sv.dhn, row0, a.n_nodes);
     __syncthreads();
     {
       float dr[8][8];
@@ -276,8 +290,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) bwd_node_kernel(const BwdNodeArgs
     // clear the scatter accumulators the edge kernels of block i-1 add into
     zero_node_rows<C>(sv.dul, row0, a.n_nodes);
     zero_node_rows<C>(sv.dur, row0, a.n_nodes);
-    zero_node_rows<D>(sv.dgx, row0, a.n_nodes);
-    zero_node_rows<D>(sv.dhn, row0, a.n_nodes);
+    if (a.red_blocked) { zero_node_rows_blocked(sv.dgx, row0); zero_node_rows_blocked(sv.dhn, row0); }
+    else { zero_node_rows<D>(sv.dgx, row0, a.n_nodes); zero_node_rows<D>(sv.dhn, row0, a.n_nodes); }
     zero_node_rows<128>(sv.dnl, row0, a.n_nodes);
     zero_node_rows<128>(sv.dnl + (size_t)a.n_nodes * 128, row0, a.n_nodes);
     zero_node_rows<32>(sv.dgn, row0, a.n_nodes);
@@ -750,13 +764,20 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
   ea.blob = net->blob; ea.tb = tb; ea.sv = sv; ea.left = plan->left; ea.right = plan->right;
   ea.n_nodes = N; ea.n_edges = E;
 
+  static const bool bwd16_env = []() { const char* e = getenv("MDB_TC_NB_BWD16"); return e == nullptr || e[0] != '0'; }();
+  auto nb_tc = [&](int blk) { return net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[blk][MDB_T_BT_NB_G2] >= 0; };
   for (int i = L - 1; i >= -1; --i) {
     // node kernel: [final] + phase B(i+1) + phase A(i)
     na.do_final = (i == L - 1);
     na.do_B = (i + 1 <= L - 1);
+    // layout of dgx / dhn: read (block i+1 scattered into them) AND re-zeroed (for block i) by this launch, so it must be
+    // the same for every block of the network -- packing.py packs the tensor-core images for all blocks or for none
+    na.red_blocked = (bwd16_env && nb_tc(L - 1)) ? 1 : 0;
     na.do_A = (i >= 0);
     if (na.do_B) { fill_blk(na.blkB, net, i + 1); na.xB = sv.x + (size_t)(i + 1) * ND; }
-    const Tables tbi = with_block_tables(tb, sv.tabs + (size_t)(i < 0 ? 0 : i) * N * TAB_FLOATS, N);
+    const int ib = i < 0 ? 0 : i;
+    const Tables tbi = with_block_tables(tb, sv.tabs + (size_t)ib * N * TAB_FLOATS, N, sv.hnb + (size_t)ib * pad64(N) * D,
+                                         sv.gxb + (size_t)ib * pad64(N) * D);
     if (na.do_A) {
       fill_blk(na.blkA, net, i);
       na.xA = sv.x + (size_t)i * ND; na.aggA = sv.agg + (size_t)i * ND;
@@ -768,9 +789,8 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     ea.tb = tbi;
     ea.e = sv.e + (size_t)i * EC; ea.sl = sv.slsr + (size_t)i * 2 * NC; ea.fl = tbi.fl; ea.fr = tbi.fr;
     LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
-    if (net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_NB_G2] >= 0) {
-      static const bool bwd16 = []() { const char* e = getenv("MDB_TC_NB_BWD16"); return e == nullptr || e[0] != '0'; }();
-      if (bwd16) {
+    if (nb_tc(i)) {
+      if (bwd16_env) {
         TcNbBwd16Args ta;
         memset(&ta, 0, sizeof(ta));
         ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;

@@ -36,6 +36,7 @@ struct HeadOff { int o[MDB_NUM_HEAD_SLOTS]; };
 // Per-node tables produced by node_kernel and gathered by the edge kernels (workspace carve-up).
 struct Tables {
   float *x, *agg, *hn, *gx, *cen;       // [N][256]
+  float *hnb, *gxb;                     // node-blocked copies of hn / gx (tile_engine.cuh: blk_off), read by the tc kernels
   float *nll, *nlr;                     // [N][128]   bond_ffn_{left,right}.node_linear(h_node)
   float *gnl, *gnr;                     // [N][32]    bond_ffn gate first layer, node + time + bias part
   float *fl, *fr;                       // [2 parities][N][64]  node_ffn_{left,right}(h_node)
@@ -157,6 +158,14 @@ __device__ __forceinline__ void store_table(const float (&acc)[8][N / 32], float
     if (n < n_rows) store_cols<N>(acc[i], table + (size_t)n * N, lane);
   }
 }
+__device__ __forceinline__ void store_table_blocked(const float (&acc)[8][8], float* __restrict__ table, int row0,
+                                                    int n_rows, int warp, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = row0 + warp * 8 + i;
+    if (n < n_rows) store_cols_blocked256(acc[i], table, n, lane);
+  }
+}
 
 // Per-node hoisted projections of one block from the h_node tile X (smem): everything a first-layer Linear
 // of the reference applies to a gathered node feature is applied per node here and gathered afterwards.
@@ -173,6 +182,7 @@ __device__ __forceinline__ void node_pre_phase(const float* __restrict__ blob, c
     tile_gemm<D, D>(acc, A, D, W_(NB_NN2_W), Ws);
     add_rowvec<D>(acc, W_(NB_NN2_B), lane);
     store_table<D>(acc, tb.hn, row0, n_nodes, warp, lane);
+    store_table_blocked(acc, tb.hnb, row0, n_nodes, warp, lane);
   }
   {  // node + time + bias part of gate.net.0 (hoisted from the per-edge cat)      graph.py:46
     float acc[8][8];
@@ -180,6 +190,7 @@ __device__ __forceinline__ void node_pre_phase(const float* __restrict__ blob, c
     add_rowvec<D>(acc, W_(NB_G1_B), lane);
     add_scaled_rowvec<D>(acc, W_(NB_GT_W), tns + warp * 8, lane);
     store_table<D>(acc, tb.gx, row0, n_nodes, warp, lane);
+    store_table_blocked(acc, tb.gxb, row0, n_nodes, warp, lane);
   }
   {  // centroid_lin(x)                                                            graph.py:51
     float acc[8][8];
@@ -706,11 +717,13 @@ int fail(int code, const char* fmt, const char* extra = "") {
   } while (0)
 
 inline size_t al(size_t n) { return (n + 31) & ~size_t(31); }
+inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }   // node-blocked tables (tile_engine.cuh: blk_off)
 
 size_t carve(Tables& tb, float* base, int64_t N, int64_t E) {
   size_t o = 0;
   auto take = [&](size_t n) { float* p = base ? base + o : nullptr; o += al(n); return p; };
   tb.x = take(N * D); tb.agg = take(N * D); tb.hn = take(N * D); tb.gx = take(N * D); tb.cen = take(N * D);
+  tb.hnb = take(pad64(N) * D); tb.gxb = take(pad64(N) * D);
   tb.nll = take(N * 128); tb.nlr = take(N * 128);
   tb.gnl = take(N * 32); tb.gnr = take(N * 32);
   tb.fl = take(2 * N * C); tb.fr = take(2 * N * C); tb.lf = take(N * C); tb.rf = take(N * C); tb.dect = take(N * C);
@@ -740,14 +753,16 @@ struct Saved {
   float *dgn;                // [2][N][32]
   float *ddect;              // [N][64]
   float *gamax;              // [32]: word 0 = bit pattern of max |d_logits| of the current backward call
+  float *hnb, *gxb;          // [L][pad64(N)][256]  node-blocked copies of the saved hn / gx tables
   float *scr_he, *scr_dm;    // [ceil(E/128)*128][256] each: tc_nodeblock_bwd16 scratch slabs (he fp32 / d msg operand planes)
 };
 
 constexpr int TAB_FLOATS = 3 * D + 2 * 128 + 2 * 32 + 2 * C;   // per node
 
 // Tables whose per-block members (hn, gx, cen, nl, gn, fl, fr) point into one saved slab
-Tables with_block_tables(const Tables& tb, float* slab, int64_t N) {
+Tables with_block_tables(const Tables& tb, float* slab, int64_t N, float* hnb, float* gxb) {
   Tables t = tb;
+  t.hnb = hnb; t.gxb = gxb;
   size_t o = 0;
   auto take = [&](size_t n) { float* p = slab + o; o += n; return p; };
   t.hn = take(N * D); t.gx = take(N * D); t.cen = take(N * D);
@@ -763,7 +778,8 @@ size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   sv.tabs = take(L * N * TAB_FLOATS);
   sv.dx = take(N * D); sv.dh = take(E * C); sv.de = take(E * C); sv.dg = take(E * G);
   sv.dul = take(N * C); sv.dur = take(N * C);
-  sv.dagg = take(N * D); sv.dgx = take(N * D); sv.dhn = take(N * D);
+  sv.dagg = take(N * D); sv.dgx = take(pad64(N) * D); sv.dhn = take(pad64(N) * D);   // dgx / dhn: row-major or node-blocked
+  sv.hnb = take(L * pad64(N) * D); sv.gxb = take(L * pad64(N) * D);
   sv.dnl = take(2 * N * 128); sv.dgn = take(2 * N * 32); sv.ddect = take(N * C);
   sv.gamax = take(32);
   const int64_t e_pad = (E + 127) / 128 * 128;
@@ -860,7 +876,11 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   const size_t NC = (size_t)N * C, ND = (size_t)N * D, EC = (size_t)E * C;
   auto sl_of = [&](int i) { return in.save ? sv.slsr + (size_t)i * 2 * NC : tb.slsr + (size_t)(i & 1) * 2 * NC; };
   // per-block view of the hoisted tables: one shared set normally, one slab per block when saving for the backward
-  auto tb_of = [&](int i) { return in.save ? with_block_tables(tb, sv.tabs + (size_t)i * N * TAB_FLOATS, N) : tb; };
+  auto tb_of = [&](int i) {
+    return in.save ? with_block_tables(tb, sv.tabs + (size_t)i * N * TAB_FLOATS, N, sv.hnb + (size_t)i * pad64(N) * D,
+                                       sv.gxb + (size_t)i * pad64(N) * D)
+                   : tb;
+  };
   auto fl_of = [&](int i) { return in.save ? tb_of(i).fl : tb.fl + (size_t)(i & 1) * NC; };
   auto fr_of = [&](int i) { return in.save ? tb_of(i).fr : tb.fr + (size_t)(i & 1) * NC; };
   HeadOff head;

@@ -44,6 +44,13 @@ __device__ __forceinline__ void store_row128(float* __restrict__ dst, const floa
 #pragma unroll
   for (int i = 0; i < 128; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
+// same into the node-blocked copy of the table (tile_engine.cuh: blk_off); lanes = consecutive nodes -> 512 B per store
+__device__ __forceinline__ void store_row128_blocked(float* __restrict__ table, int n, int c0, const float (&v)[128]) {
+  float* dst = table + blk_off(n, c0 / 4);
+#pragma unroll
+  for (int i = 0; i < 128; i += 4)
+    *reinterpret_cast<float4*>(dst + (i / 4) * BLK_PIECE_STRIDE) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
 template <int NC>
 __device__ __forceinline__ void store_rowN(float* __restrict__ dst, const float (&v)[NC]) {
 #pragma unroll
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_node_kernel(const __grid_
       load_half_row(lane_base + D0 + hc, v);
 #pragma unroll
       for (int i = 0; i < 128; ++i) v[i] += a.v.gx_b[hc + i] + tnv * a.v.gx_t[hc + i];
-      if (valid) store_row128(tp.gx + nn * D + hc, v);
+      if (valid) { store_row128(tp.gx + nn * D + hc, v); store_row128_blocked(tp.gxb, n, hc, v); }
       load_half_row(lane_base + D1 + hc, v);
       add_vec128(v, a.v.cen_b + hc);
       if (valid) store_row128(tp.cen + nn * D + hc, v);
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_node_kernel(const __grid_
       float v[128];
       load_half_row(lane_base + D0 + hc, v);
       add_vec128(v, a.v.nn2_b + hc);
-      if (valid) store_row128(tp.hn + nn * D + hc, v);
+      if (valid) { store_row128(tp.hn + nn * D + hc, v); store_row128_blocked(tp.hnb, n, hc, v); }
     }
   }
 

@@ -33,7 +33,7 @@ struct TcNbBwd16Args {
   int n_nodes, n_edges;
   const float* e;        // [E][64] saved e_i
   const float* dagg;     // [N][256] d/d (aggregated messages)
-  float *dgx, *dhn;      // [N][256] scatter targets (pre-zeroed)
+  float *dgx, *dhn;      // [pad64(N)][256] scatter targets (pre-zeroed), NODE-BLOCKED layout (tile_engine.cuh: blk_off)
   float* de;             // [E][64]  d/d e, accumulated (+=)
   float* scr_he;         // [tiles * 128][256] fp32 scratch
   uint8_t* scr_dm;       // [tiles][2][64 KB] d msg as A-operand planes
@@ -50,6 +50,17 @@ __device__ __forceinline__ Row16 ld_row16(const float* __restrict__ p) {
   for (int j = 0; j < 4; ++j) r.v[j] = *reinterpret_cast<const float4*>(p + 4 * j);
   return r;
 }
+// chunk c (16 columns = four 16-byte pieces, PS floats apart) of this thread's row in a blocked layout: the tile-blocked
+// he scratch (PS = 512) or a node-blocked table (PS = BLK_PIECE_STRIDE)
+template <int PS>
+__device__ __forceinline__ Row16 ld_blk16(const float* __restrict__ base, int c) {
+  Row16 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r.v[j] = *reinterpret_cast<const float4*>(base + (c * 4 + j) * PS);
+  return r;
+}
+__device__ __forceinline__ Row16 ld_he16(const float* __restrict__ base, int c) { return ld_blk16<tc::ROWS * 4>(base, c); }
+__device__ __forceinline__ Row16 ld_tab16(const float* __restrict__ base, int c) { return ld_blk16<BLK_PIECE_STRIDE>(base, c); }
 __device__ __forceinline__ void unpack_row16(const Row16& r, float (&x)[16]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) { x[4 * j] = r.v[j].x; x[4 * j + 1] = r.v[j].y; x[4 * j + 2] = r.v[j].z; x[4 * j + 3] = r.v[j].w; }
@@ -114,9 +125,11 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   TC_STAMP(1);
   const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t A0 = lane_base + pc, A1 = lane_base + 256 + pc;
-  const float* hn = tb.hn + (size_t)rr * D + pc;
-  const float* gxr = tb.gx + (size_t)rr * D + pc;
-  float* he_scr = a.scr_he + (size_t)q * D + pc;                   // q < tiles * 128 always
+  const float* hn = tb.hnb + blk_off(rr, pc / 4);      // node-blocked tables (tile_engine.cuh): coalesced gathers / REDs
+  const float* gxr = tb.gxb + blk_off(rr, pc / 4);
+  // he scratch, tile-blocked so that a warp instruction (32 consecutive rows, one 16-byte piece each) touches 4 lines
+  // instead of 32: [tile][16-byte column piece 0..63][row 0..127][4 floats]
+  float* he_scr = a.scr_he + (size_t)blockIdx.x * tc::ROWS * D + (size_t)(pc / 4) * tc::ROWS * 4 + row * 4;
   uint8_t* dm_scr = a.scr_dm + (size_t)blockIdx.x * 2 * PLANE256_BYTES;
   float2 ms_en1 = make_float2(0.f, 1.f), ms_g1 = make_float2(0.f, 1.f);
   float de16[16];
@@ -156,21 +169,21 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   }
   tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_EN2), 0, false, true, true);          // he -> A0
   if (IS_ROW) {
-    Row16 nx = ld_row16(hn);                     // first chunk of hn[r]: in flight while the GEMM runs
+    Row16 nx = ld_tab16(hn, 0);                     // first chunk of hn[r]: in flight while the GEMM runs
     tc::rows_wait_acc(p);
     TC_STAMP(5);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       float x[16], b[16], h[16];
       unpack_row16(nx, h);
-      if (c < 3) nx = ld_row16(hn + (c + 1) * 16);
+      if (c < 3) nx = ld_tab16(hn, c + 1);
       tc::tmem_ld16(A0 + c * 16, x);
       lds16(v_en2_b + pc + c * 16, b);
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] += b[i];
 #pragma unroll
       for (int i = 0; i < 16; i += 4)            // he: needed again by the message branch
-        *reinterpret_cast<float4*>(he_scr + c * 16 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+        *reinterpret_cast<float4*>(he_scr + (c * 4 + i / 4) * tc::ROWS * 4) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] *= h[i];
       store_a16(x_hi, x_lo, row, pc + c * 16, x);
@@ -181,7 +194,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_MSG), 256, false, true, false);        // msg -> A1
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), 0, false, false, true);                       // a3 - gx -> A0
   if (IS_ROW) {
-    Row16 nx = ld_row16(gxr);
+    Row16 nx = ld_tab16(gxr, 0);
     tc::rows_wait_acc(p);
     TC_STAMP(7);
     RunStat rs = {0.f, 0.f, 0.f};
@@ -189,7 +202,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
     for (int c = 0; c < 4; ++c) {                // fold gx[r] into the accumulator; statistics
       float x[16], g[16];
       unpack_row16(nx, g);
-      if (c < 3) nx = ld_row16(gxr + (c + 1) * 16);
+      if (c < 3) nx = ld_tab16(gxr, c + 1);
       tc::tmem_ld16(A0 + c * 16, x);
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] += g[i];
@@ -242,7 +255,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(BT_NB_G2), 256, false, true, false);                  // d r3 -> A1
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), 0, false, false, true);                       // a3 - gx -> A0 (again)
   if (IS_ROW) {
-    Row16 nx = ld_row16(gxr);
+    Row16 nx = ld_tab16(gxr, 0);
     tc::rows_wait_acc(p);
     TC_STAMP(11);
     float s1 = 0.f, s2 = 0.f;
@@ -250,7 +263,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
     for (int c = 0; c < 4; ++c) {                // pass 1: a3 = acc + gx (folded back) ; d xhat -> A1 ; partial sums
       float x[16], g[16], d[16], ga[16], be[16];
       unpack_row16(nx, g);
-      if (c < 3) nx = ld_row16(gxr + (c + 1) * 16);
+      if (c < 3) nx = ld_tab16(gxr, c + 1);
       tc::tmem_ld16(A0 + c * 16, x);
       tc::tmem_ld16(A1 + c * 16, d);
       lds16(v_g1_g + pc + c * 16, ga); lds16(v_g1_be + pc + c * 16, be);
@@ -273,7 +286,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
     const float2 t0 = stat[row], t1 = stat[tc::ROWS + row], t2 = stat[2 * tc::ROWS + row], t3 = stat[3 * tc::ROWS + row];
     asm volatile("bar.sync 1, 512;" ::: "memory");
     const float m1 = ((t0.x + t1.x) + (t2.x + t3.x)) * (1.f / 256.f), m2 = ((t0.y + t1.y) + (t2.y + t3.y)) * (1.f / 256.f);
-    float* dst = a.dgx + (size_t)rr * D + pc;
+    float* dst = a.dgx + blk_off(rr, pc / 4);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {                // pass 2: d a3 -> dgx[r] (RED) and the X planes
       float x[16], d[16];
@@ -286,7 +299,8 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
       }
       if (valid) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) tc::red_add_v4(dst + c * 16 + i, d[i], d[i + 1], d[i + 2], d[i + 3]);
+        for (int i = 0; i < 16; i += 4)
+          tc::red_add_v4(dst + (c * 4 + i / 4) * BLK_PIECE_STRIDE, d[i], d[i + 1], d[i + 2], d[i + 3]);
       }
       store_a16(x_hi, x_lo, row, pc + c * 16, d);
     }
@@ -313,20 +327,21 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
     TC_STAMP(13);
     tc::tmem_ld16(lane_base + part * 16, de16);
     tc::rows_publish(p);                         // keeps the `done` barrier at most one phase ahead of the row threads
-    Row16 nh = ld_row16(hn), ne = ld_row16(he_scr);
+    Row16 nh = ld_tab16(hn, 0), ne = ld_he16(he_scr, 0);
     tc::rows_wait_acc(p);                        // BT_NB_MSG
     TC_STAMP(14);
-    float* dst = a.dhn + (size_t)rr * D + pc;
+    float* dst = a.dhn + blk_off(rr, pc / 4);
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       float dm[16], h[16], he[16];
       unpack_row16(nh, h); unpack_row16(ne, he);
-      if (c < 3) { nh = ld_row16(hn + (c + 1) * 16); ne = ld_row16(he_scr + (c + 1) * 16); }
+      if (c < 3) { nh = ld_tab16(hn, c + 1); ne = ld_he16(he_scr, c + 1); }
       tc::tmem_ld16(A1 + c * 16, dm);
       if (valid) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          tc::red_add_v4(dst + c * 16 + i, dm[i] * he[i], dm[i + 1] * he[i + 1], dm[i + 2] * he[i + 2], dm[i + 3] * he[i + 3]);
+          tc::red_add_v4(dst + (c * 4 + i / 4) * BLK_PIECE_STRIDE, dm[i] * he[i], dm[i + 1] * he[i + 1], dm[i + 2] * he[i + 2],
+                         dm[i + 3] * he[i + 3]);
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) dm[i] *= h[i];           // d he

@@ -39,6 +39,20 @@ __device__ __forceinline__ int col_of(int lane, int j) {
   else return lane;
 }
 
+// Node-blocked layout of a [n_nodes][256] per-node table: [node / 32][16-byte column piece 0..63][node % 32][4 floats].
+// A warp whose lanes hold (mostly) consecutive nodes -- the tensor-core edge kernels: one thread per CSR-ordered edge,
+// gathering by `right` -- then touches ~4 cache lines per 16-byte load / RED instead of 32 (row-major rows are 1 KB
+// apart), which is what bounded their epilogues (LSU tag stage: one line per cycle).  Tables are padded to 64 nodes.
+__host__ __device__ __forceinline__ size_t blk_off(int n, int piece) {
+  return ((size_t)(n >> 5) * 64 + piece) * 128 + (size_t)(n & 31) * 4;
+}
+constexpr int BLK_PIECE_STRIDE = 128;   // floats between consecutive 16-byte pieces of the same node
+// this lane's 8 columns (pieces lane and 32 + lane) of node n
+__device__ __forceinline__ void store_cols_blocked256(const float (&v)[8], float* table, int n, int lane) {
+  *reinterpret_cast<float4*>(table + blk_off(n, lane)) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(table + blk_off(n, 32 + lane)) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 // Load / store this lane's N/32 columns of one row (row pointer p, 16-byte aligned rows).
 template <int N>
 __device__ __forceinline__ void load_cols(float (&v)[N / 32], const float* p, int lane) {

@@ -33,11 +33,11 @@ torch.cuda.synchronize()
 lib.mdb_debug_set_buffer(None)
 t = buf.view(tiles, 32).cpu().numpy().astype(np.int64)
 names = ["set-up", "e tile -> planes",
-         "wait EN1", "epi LN(en1)", "wait EN2", "epi *hn", "wait MSG+GE", "epi LN(g1)+gx", "wait G2", "epi dout: dmsg, dgate",
-         "wait BT_G2", "drain d relu3", "wait GE", "epi a3 fold + LN bwd + RED dgx", "wait BT_GE", "epi de + dmsg->planes",
-         "wait BT_MSG+EN1", "epi LN(en1) again", "wait EN2 (he)", "epi dhn RED + d he", "wait BT_EN2+EN1", "epi LN bwd (en1)",
-         "wait BT_EN1", "epi de out"]
-d = t[:, 1:25] - t[:, 0:24]
+         "wait EN1", "epi LN(en1)", "wait EN2", "epi he*hn (+he scratch)", "wait MSG+GE", "epi LN(g1)+gx", "wait G2",
+         "epi dout: dgt->planes, dmsg->scratch", "wait BT_G2+GE", "epi LN bwd(g1) + RED dgx", "wait BT_GE", "de -> regs",
+         "wait reload+BT_MSG", "epi dhn RED + d he", "wait BT_EN2+EN1", "epi LN bwd(en1)", "wait BT_EN1", "epi de out"]
+NS = len(names)
+d = t[:, 1:NS + 1] - t[:, 0:NS]
 print(f"tiles {tiles}; per-tile cycles mean / median / p90 (last launch = block 0 of the bond predictor backward)")
 wait = epi = 0
 for i, n in enumerate(names):
@@ -46,5 +46,5 @@ for i, n in enumerate(names):
         wait += d[:, i].mean()
     else:
         epi += d[:, i].mean()
-tot = t[:, 24] - t[:, 0]
+tot = t[:, NS] - t[:, 0]
 print(f"  {'total':34s} {tot.mean():9.0f} {np.median(tot):9.0f} {np.percentile(tot, 90):9.0f}   waits {wait:.0f}  epilogues+setup {epi:.0f}")
