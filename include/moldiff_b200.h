@@ -214,7 +214,7 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
   X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
-  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node)
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,
@@ -222,6 +222,24 @@ enum mdb_kernel_class {
 #undef MDB_X
   MDB_NUM_KERNEL_CLASSES
 };
+
+/*
+ * mdb_transition_step <- the posterior-sampling block of MolDiff.sample between two denoiser evaluations
+ *   (models/model.py:287-300,365-372; models/transition.py:44-63,285-315; models/diffusion.py:79-85), discrete
+ *   categorical space: positions via the Gaussian posterior, node / half-edge types via the categorical posterior +
+ *   Gumbel-max, one-hot encodings of the sampled classes (half-edges doubled to the [2 Eh, Ke] directed list).
+ * t [n_graphs] int64; pos, pred_pos, z_pos [N,3]; pred_node, log_node, u_node [N,Kn]; pred_half, log_half, u_half
+ * [Eh,Ke]; coef_x0, coef_xt, std [T]; q*_cum = q_mats [T,K,K]; q*_stepT = transpopse_q_onestep_mats [T,K,K].
+ * z_pos ~ N(0,1) and u_* ~ U[0,1) are drawn by the caller.  Outputs: pos_out [N,3], log_node_out / h_node_out [N,Kn],
+ * log_half_out [Eh,Ke], h_edge_out [2 Eh,Ke], half_type_out [Eh] int64 (may be NULL).  Kn, Ke <= 16.
+ */
+int mdb_transition_step(int32_t n_nodes, int32_t n_half, int32_t kn, int32_t ke, const int64_t* batch_node,
+                        const int64_t* batch_half, const int64_t* t, const float* pos, const float* pred_pos,
+                        const float* z_pos, const float* coef_x0, const float* coef_xt, const float* std_, float* pos_out,
+                        const float* pred_node, const float* log_node, const float* u_node, const float* qn_cum,
+                        const float* qn_stepT, float* log_node_out, float* h_node_out, const float* pred_half,
+                        const float* log_half, const float* u_half, const float* qe_cum, const float* qe_stepT,
+                        float* log_half_out, float* h_edge_out, int64_t* half_type_out, void* stream);
 
 /* Profiling: between begin and end every kernel launch of this library is bracketed by CUDA events on
  * its own stream; end synchronises those events and returns summed milliseconds / launch counts per

@@ -1004,6 +1004,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 
 #include "mdb_backward.cuh"
 #include "tc_selftest.cuh"
+#include "mdb_transition.cuh"
 
 }  // namespace
 
@@ -1041,6 +1042,34 @@ int mdb_moldiff_forward(const mdb_net_desc* net, const mdb_plan* plan, const flo
   in.batch_node = batch_node; in.batch_edge = batch_edge; in.t = t;
   in.out_node = pred_node; in.out_pos = pred_pos; in.out_edge = pred_halfedge;
   return run_forward(net, plan, in, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mdb_transition_step(int32_t n_nodes, int32_t n_half, int32_t kn, int32_t ke, const int64_t* batch_node,
+                        const int64_t* batch_half, const int64_t* t, const float* pos, const float* pred_pos,
+                        const float* z_pos, const float* coef_x0, const float* coef_xt, const float* std_, float* pos_out,
+                        const float* pred_node, const float* log_node, const float* u_node, const float* qn_cum,
+                        const float* qn_stepT, float* log_node_out, float* h_node_out, const float* pred_half,
+                        const float* log_half, const float* u_half, const float* qe_cum, const float* qe_stepT,
+                        float* log_half_out, float* h_edge_out, int64_t* half_type_out, void* stream) {
+  if (n_nodes < 0 || n_half < 0 || kn < 1 || ke < 1 || kn > 16 || ke > 16) return fail(MDB_EINVAL, "mdb_transition_step: bad sizes%s");
+  if (n_nodes + n_half == 0) return MDB_OK;
+  TransArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_nodes = n_nodes; a.n_half = n_half; a.kn = kn; a.ke = ke;
+  a.batch_node = batch_node; a.batch_half = batch_half; a.t = t;
+  a.pos = pos; a.pred_pos = pred_pos; a.z_pos = z_pos; a.coef_x0 = coef_x0; a.coef_xt = coef_xt; a.stdv = std_; a.pos_out = pos_out;
+  a.pred_node = pred_node; a.log_node = log_node; a.u_node = u_node; a.qn_cum = qn_cum; a.qn_stepT = qn_stepT;
+  a.log_node_out = log_node_out; a.h_node_out = h_node_out;
+  a.pred_half = pred_half; a.log_half = log_half; a.u_half = u_half; a.qe_cum = qe_cum; a.qe_stepT = qe_stepT;
+  a.log_half_out = log_half_out; a.h_edge_out = h_edge_out; a.half_type_out = half_type_out;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int total = n_nodes + n_half;
+  if (kn == 8 && ke == 6) {          // the reference's type counts (utils/transforms.py:22-23)
+    LAUNCH(MDB_K_transition, st, (transition_step_kernel<8, 6><<<(total + 255) / 256, 256, 0, st>>>(a)));
+  } else {
+    LAUNCH(MDB_K_transition, st, (transition_step_kernel<0, 0><<<(total + 255) / 256, 256, 0, st>>>(a)));
+  }
+  return MDB_OK;
 }
 
 int mdb_bondpred_forward(const mdb_net_desc* net, const mdb_plan* plan, const float* h_node, const float* pos,

@@ -88,6 +88,7 @@ class MolDiff(nn.Module, _PackedMixin):
         self.time_dim = time_dim
         self._packed = None
         self._packed_key = None
+        self.fused_transition = True     # CUDA tensors: posterior sampling in one launch (False = unfused PyTorch ops)
 
     # ---- weights ----
     def _pack(self, device):
@@ -231,13 +232,26 @@ class MolDiff(nn.Module, _PackedMixin):
         batch_node, batch_halfedge = st["batch_node"], st["batch_halfedge"]
         h_node, pos, h_half = st["h_node"], st["pos"], st["h_half"]
         time_step = torch.full((st["n_graphs"],), step, dtype=torch.long, device=device)
-        preds = self(h_node, pos, batch_node, torch.cat([h_half, h_half], dim=0), st["edge_index"],
-                     st["batch_edge"], time_step)
+        h_edge = st.pop("h_edge2", None)              # [2 Eh, Ke] written directly by the fused transition step
+        if h_edge is None or h_edge.data_ptr() != h_half.data_ptr():   # (stale if the caller replaced st["h_half"])
+            h_edge = torch.cat([h_half, h_half], dim=0)
+        preds = self(h_node, pos, batch_node, h_edge, st["edge_index"], st["batch_edge"], time_step)
         pred_node, pred_pos, pred_half = preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]
 
-        pos_prev = self.pos_transition.get_prev_from_recon(x_t=pos, x_recon=pred_pos, t=time_step, batch=batch_node)
         half_type_prev = None
-        if discrete:
+        fused = discrete and pos.is_cuda and self.fused_transition
+        if fused:
+            # one CUDA launch for the whole posterior-sampling block (csrc/mdb_transition.cuh)
+            pos_prev, st["log_node"], h_node_prev, st["log_half"], h_edge2, half_type_prev = engine.transition_step(
+                self.pos_transition, self.node_transition, self.edge_transition, time_step, batch_node, batch_halfedge,
+                pos, pred_pos, pred_node, st["log_node"], pred_half, st["log_half"])
+            h_half_prev = h_edge2[: h_half.shape[0]]
+            st["h_edge2"] = h_edge2
+        else:
+            pos_prev = self.pos_transition.get_prev_from_recon(x_t=pos, x_recon=pred_pos, t=time_step, batch=batch_node)
+        if fused:
+            pass                                      # everything below was produced by the fused launch
+        elif discrete:
             st["log_node"] = self.node_transition.q_v_posterior(F.log_softmax(pred_node, dim=-1), st["log_node"],
                                                                 time_step, batch_node, v0_prob=True)
             h_node_prev = self.node_transition.onehot_encode(gumbel_argmax(st["log_node"]))

@@ -90,6 +90,8 @@ def load_library():
         lib.mdb_bondpred_backward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 8 + [sz, vp]
         lib.mdb_tc_selftest.restype = C.c_int
         lib.mdb_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        lib.mdb_transition_step.restype = C.c_int
+        lib.mdb_transition_step.argtypes = [i32, i32, i32, i32] + [vp] * 26
         lib.mdb_profile_begin.restype = None
         lib.mdb_profile_end.restype = C.c_int
         lib.mdb_profile_end.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -315,6 +317,43 @@ def moldiff_forward(net: PackedNet, plan: GraphPlan, h_node_pert, pos_pert, h_ed
                                  ws.data_ptr(), ws.numel() * 4, _stream_ptr(dev))
     _check(rc, "mdb_moldiff_forward")
     return pred_node, pred_pos, pred_half
+
+
+def transition_step(pos_tr, node_tr, edge_tr, t, batch_node, batch_half, pos, pred_pos, pred_node, log_node,
+                    pred_half, log_half):
+    """One fused reverse-transition step of the sampler (`mdb_transition_step`): Gaussian posterior for the positions,
+    categorical posteriors + Gumbel-max for node / half-edge types.  The random variates are drawn here from torch's
+    generator in the order the unfused PyTorch path consumes them (positions, node types, half-edge types).
+    Returns (pos_prev, log_node, h_node_prev, log_half, h_edge_prev [2 Eh, Ke], half_type_prev [Eh])."""
+    lib = load_library()
+    pos, pred_pos = _dev_f32(pos, "pos"), _dev_f32(pred_pos, "pred_pos")
+    pred_node, log_node = _dev_f32(pred_node, "pred_node"), _dev_f32(log_node, "log_node")
+    pred_half, log_half = _dev_f32(pred_half, "pred_halfedge"), _dev_f32(log_half, "log_halfedge")
+    batch_node, batch_half, t = _dev_i64(batch_node, "batch_node"), _dev_i64(batch_half, "batch_halfedge"), _dev_i64(t, "t")
+    N, Eh = pos.shape[0], pred_half.shape[0]
+    kn, ke = pred_node.shape[1], pred_half.shape[1]
+    if kn != node_tr.num_classes or ke != edge_tr.num_classes or kn > 16 or ke > 16:
+        raise MoldiffB200Error("transition_step: class counts do not match the transitions (or exceed 16)")
+    dev = pos.device
+    z_pos = torch.randn_like(pos)
+    u_node = torch.rand_like(pred_node)
+    u_half = torch.rand_like(pred_half)
+    pos_out = torch.empty_like(pos)
+    log_node_out, h_node_out = torch.empty_like(log_node), torch.empty_like(log_node)
+    log_half_out = torch.empty_like(log_half)
+    h_edge_out = torch.empty(2 * Eh, ke, dtype=torch.float32, device=dev)
+    half_type = torch.empty(Eh, dtype=torch.int64, device=dev)
+    tabs = [pos_tr.coef_x0, pos_tr.coef_xt, pos_tr.std, node_tr.q_mats, node_tr.transpopse_q_onestep_mats,
+            edge_tr.q_mats, edge_tr.transpopse_q_onestep_mats]
+    c0, ct, sd, qn, qnt, qe, qet = [_dev_f32(x.detach(), "transition table") for x in tabs]
+    rc = lib.mdb_transition_step(
+        N, Eh, kn, ke, batch_node.data_ptr(), batch_half.data_ptr(), t.data_ptr(), pos.data_ptr(), pred_pos.data_ptr(),
+        z_pos.data_ptr(), c0.data_ptr(), ct.data_ptr(), sd.data_ptr(), pos_out.data_ptr(), pred_node.data_ptr(),
+        log_node.data_ptr(), u_node.data_ptr(), qn.data_ptr(), qnt.data_ptr(), log_node_out.data_ptr(), h_node_out.data_ptr(),
+        pred_half.data_ptr(), log_half.data_ptr(), u_half.data_ptr(), qe.data_ptr(), qet.data_ptr(), log_half_out.data_ptr(),
+        h_edge_out.data_ptr(), half_type.data_ptr(), _stream_ptr(dev))
+    _check(rc, "mdb_transition_step")
+    return pos_out, log_node_out, h_node_out, log_half_out, h_edge_out, half_type
 
 
 def bondpred_forward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, batch_edge, t, save=False):
