@@ -66,6 +66,16 @@ __device__ __forceinline__ void ln_relu_part(float (&v)[NC], const float* __rest
   for (int i = 0; i < NC; ++i) v[i] = fmaxf((v[i] - mean) * rstd * gamma[i] + beta[i], 0.f);
 }
 
+// NC floats of a gathered table row -> registers (issued BEFORE the accumulator wait so the L2 latency hides behind the GEMM)
+template <int NC>
+__device__ __forceinline__ void gather_n(const float* __restrict__ src, float (&v)[NC]) {
+#pragma unroll
+  for (int i = 0; i < NC; i += 4) {
+    const float4 t4 = *reinterpret_cast<const float4*>(src + i);
+    v[i] = t4.x; v[i + 1] = t4.y; v[i + 2] = t4.z; v[i + 3] = t4.w;
+  }
+}
+
 constexpr int FFN_O_LD = 68;    // fp32 row stride of the o tile: 272 B = 16 (mod 128)
 
 __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const __grid_constant__ TcFfnArgs a) {
@@ -155,28 +165,21 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
     if (p.role == 0) {
       const float* nl = (side ? tb.nlr : tb.nll) + (size_t)node * 128 + half * 64;
       const float* gn = (side ? tb.gnr : tb.gnl) + (size_t)node * 32 + half * 16;
+      float nlv[64], gnv[16];
+      gather_n<64>(nl, nlv); gather_n<16>(gn, gnv);
       tc::rows_wait_acc(p);
       {
         float v[64];
         load_cols_tm<64>(lane_base + half * 64, v);
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(nl + i);
-          v[i] *= t4.x; v[i + 1] *= t4.y; v[i + 2] *= t4.z; v[i + 3] *= t4.w;       // * node_linear(h_node)[.]
-        }
+        for (int i = 0; i < 64; ++i) v[i] *= nlv[i];                                 // * node_linear(h_node)[.]
         tc::store_a<128, 64>(a_hi, a_lo, row, half * 64, v);
       }
       {
         float g[16];
         load_cols_tm<16>(lane_base + 128 + half * 16, g);
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(gn + i);
-          g[i] += t4.x + te * sv.gt_w[half * 16 + i];
-          g[i + 1] += t4.y + te * sv.gt_w[half * 16 + i + 1];
-          g[i + 2] += t4.z + te * sv.gt_w[half * 16 + i + 2];
-          g[i + 3] += t4.w + te * sv.gt_w[half * 16 + i + 3];
-        }
+        for (int i = 0; i < 16; ++i) g[i] += gnv[i] + te * sv.gt_w[half * 16 + i];
         ln_relu_part<16>(g, sv.g1_g + half * 16, sv.g1_be + half * 16, stat, row, half);
         tc::store_a<32, 16>(g_hi, g_lo, row, half * 16, g);
       }
@@ -394,26 +397,19 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_bwd_kernel(const 
     tc::gemm<C, 32>(p, e_hi, e_lo, w_gb, T_G1, false, false, true);
     float xh6[16], rstd6 = 0.f;
     if (p.role == 0) {
+      float nlv[64], gnv[16];
+      gather_n<64>(nl, nlv); gather_n<16>(gn, gnv);
       tc::rows_wait_acc(p);
       {
         float v[64];
         load_cols_tm<64>(lane_base + T_BL + half * 64, v);
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(nl + i);
-          v[i] *= t4.x; v[i + 1] *= t4.y; v[i + 2] *= t4.z; v[i + 3] *= t4.w;
-        }
+        for (int i = 0; i < 64; ++i) v[i] *= nlv[i];
         tc::store_a<128, 64>(a_hi, a_lo, row, half * 64, v);
       }
       load_cols_tm<16>(lane_base + T_G1 + half * 16, xh6);
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 t4 = *reinterpret_cast<const float4*>(gn + i);
-        xh6[i] += t4.x + te * sv.gt_w[half * 16 + i];
-        xh6[i + 1] += t4.y + te * sv.gt_w[half * 16 + i + 1];
-        xh6[i + 2] += t4.z + te * sv.gt_w[half * 16 + i + 2];
-        xh6[i + 3] += t4.w + te * sv.gt_w[half * 16 + i + 3];
-      }
+      for (int i = 0; i < 16; ++i) xh6[i] += gnv[i] + te * sv.gt_w[half * 16 + i];
       rstd6 = ln_xhat_part<16>(xh6, stat, row, half);
       float r6[16];
 #pragma unroll
@@ -445,22 +441,19 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_bwd_kernel(const 
     // ---- d o = DUL[r] (left FFN, scattered over right) / DUR[l] (right FFN, scattered over left)
     if (p.role == 0) {
       const float* du = (side ? a.dur : a.dul) + (size_t)other * C + half * 32;
+      float duv[32];
+      gather_n<32>(du, duv);                                  // (`other` is 0 for padding rows: a valid address)
       tc::rows_wait_acc(p);
       float i2[32];
       tc::tmem_ld32(lane_base + T_I2 + half * 32, i2);
       float dgg[32];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) d4 = *reinterpret_cast<const float4*>(du + i);
-        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float s = sgg[i + u];
-          const float val = i2[i + u] + sv.i2_b[half * 32 + i + u];
-          dgg[i + u] = dd[u] * val * s * (1.f - s);
-          i2[i + u] = dd[u] * s;                              // d i2
-        }
+      for (int i = 0; i < 32; ++i) {
+        const float dd = valid ? duv[i] : 0.f;
+        const float s = sgg[i];
+        const float val = i2[i] + sv.i2_b[half * 32 + i];
+        dgg[i] = dd * val * s * (1.f - s);
+        i2[i] = dd * s;                                       // d i2
       }
       tc::store_a<C, 32>(s1_hi, s1_lo, row, half * 32, dgg);   // (the K = 128 A planes are dead: r5 was consumed)
       tc::store_a<C, 32>(s2_hi, s2_lo, row, half * 32, i2);
