@@ -75,18 +75,19 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_edge_d_kernel(const __gri
     const float* t1 = a.sl + (size_t)a.n_nodes * C + (size_t)rr * C + c32;  // scatter_sum(msg_right, left)[right]
     const float* t2 = a.fl + (size_t)ll * C + c32;
     const float* t3 = a.fr + (size_t)rr * C + c32;
-    tc::rows_wait_acc(p);
-    float u[32];
-    tc::tmem_ld32(lane_base + c32, u);
+    float gsum[32];                                          // the four gathered rows, summed while the GEMM runs
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 x0 = *reinterpret_cast<const float4*>(t0 + i), x1 = *reinterpret_cast<const float4*>(t1 + i);
       const float4 x2 = *reinterpret_cast<const float4*>(t2 + i), x3 = *reinterpret_cast<const float4*>(t3 + i);
-      u[i] += a.v.self_b[c32 + i] + x0.x + x1.x + x2.x + x3.x;
-      u[i + 1] += a.v.self_b[c32 + i + 1] + x0.y + x1.y + x2.y + x3.y;
-      u[i + 2] += a.v.self_b[c32 + i + 2] + x0.z + x1.z + x2.z + x3.z;
-      u[i + 3] += a.v.self_b[c32 + i + 3] + x0.w + x1.w + x2.w + x3.w;
+      gsum[i] = x0.x + x1.x + x2.x + x3.x; gsum[i + 1] = x0.y + x1.y + x2.y + x3.y;
+      gsum[i + 2] = x0.z + x1.z + x2.z + x3.z; gsum[i + 3] = x0.w + x1.w + x2.w + x3.w;
     }
+    tc::rows_wait_acc(p);
+    float u[32];
+    tc::tmem_ld32(lane_base + c32, u);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) u[i] += a.v.self_b[c32 + i] + gsum[i];
     ln_relu_part<32>(u, a.v.ln_g + c32, a.v.ln_be + c32, stat, row, half);
     tc::store_a<C, 32>(p_hi, p_lo, row, c32, u);
     tc::rows_publish(p);
@@ -96,6 +97,16 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_edge_d_kernel(const __gri
   float rel = 0.f, dist = 1.f;                               // half 0: x / half 1: y, and z handled by half 0 too
   float relz = 0.f;
   if (p.role == 0) {
+    float pv[32];                                            // left_feat * right_feat (PosUpdate): gathered before the wait
+    if (a.update_pos) {
+      const float* lf = tb.lf + (size_t)ll * C + c32;
+      const float* rf = tb.rf + (size_t)rr * C + c32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(lf + i), y = *reinterpret_cast<const float4*>(rf + i);
+        pv[i] = x.x * y.x; pv[i + 1] = x.y * y.y; pv[i + 2] = x.z * y.z; pv[i + 3] = x.w * y.w;
+      }
+    }
     tc::rows_wait_acc(p);
     float h[32];
     tc::tmem_ld32(lane_base + c32, h);
@@ -108,14 +119,6 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_edge_d_kernel(const __gri
     }
     if (a.update_pos) {
       tc::store_a<C, 32>(h_hi, h_lo, row, c32, h);                          // e planes are dead: reuse for new h_edge
-      const float* lf = tb.lf + (size_t)ll * C + c32;
-      const float* rf = tb.rf + (size_t)rr * C + c32;
-      float pv[32];
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 x = *reinterpret_cast<const float4*>(lf + i), y = *reinterpret_cast<const float4*>(rf + i);
-        pv[i] = x.x * y.x; pv[i + 1] = x.y * y.y; pv[i + 2] = x.z * y.z; pv[i + 3] = x.w * y.w;   // left_feat * right_feat
-      }
       tc::store_a<C, 32>(p_hi, p_lo, row, c32, pv);
       const float dx = a.pos_cur[ll * 3 + 0] - a.pos_cur[rr * 3 + 0];
       const float dy = a.pos_cur[ll * 3 + 1] - a.pos_cur[rr * 3 + 1];
