@@ -56,6 +56,16 @@ def peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel class, from the committed
+    `ncu --set full` capture of this round (profiles/r01_ncu_metrics.json, written by tools/ncu_metrics.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_metrics.json")) as f:
+            return {k: v.get("traffic_bytes") for k, v in json.load(f).items()}
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -272,8 +282,13 @@ def main():
         avg_ms = info["ms_total"] / max(info["launches"], 1)
         flop = engine.KERNEL_LOGICAL_FLOP_PER_EDGE.get(name, 0.0) * E
         achieved = flop / (avg_ms * 1e-3) / 1e12
+        traffic = ncu_traffic()
+        per_kernel_tf = {k: round(engine.KERNEL_LOGICAL_FLOP_PER_EDGE[k] * E * v["launches"] / (v["ms_total"] * 1e-3) / 1e12, 2)
+                         for k, v in prof.items() if k in engine.KERNEL_LOGICAL_FLOP_PER_EDGE and v["ms_total"] > 0}
         roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " (sustained bf16)",
+                "frac": achieved / pk["tf_sust"], "traffic": traffic.get(name), "peak_source": pk["src"] + " (sustained bf16)",
+                "traffic_source": "profiles/r01_ncu_metrics.json (ncu --set full, one launch)" if traffic.get(name) else None,
+                "per_kernel_tflops_as_written": per_kernel_tf,
                 "avg_launch_ms": avg_ms, "note": "achieved = reference-as-written GEMM FLOPs of the layer part this kernel computes / CUDA-event time; "
                         "tc_* kernels execute them as 3 split-bf16 tcgen05 MMAs after per-node hoisting, others as fp32 FFMA",
                 "hbm_algorithmic_gbs": (512.0 * E + 2080.0 * N) / (avg_ms * 1e-3) / 1e9,

@@ -799,7 +799,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
         ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
         ta.scr_he = sv.scr_he; ta.scr_dm = reinterpret_cast<uint8_t*>(sv.scr_dm);
         LAUNCH(MDB_K_tc_nodeblock_bwd, st,
-               (tc_nodeblock_bwd16_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, NB16_THREADS, SMEM_TC_NB_BWD16, st>>>(ta)));
+               (tc_nodeblock_bwd16_kernel<<<persistent_grid((E + tc::ROWS - 1) / tc::ROWS), NB16_THREADS, SMEM_TC_NB_BWD16, st>>>(ta)));
       } else {
         TcNbBwdArgs ta;
         memset(&ta, 0, sizeof(ta));

@@ -717,6 +717,15 @@ int fail(int code, const char* fmt, const char* extra = "") {
   } while (0)
 
 inline size_t al(size_t n) { return (n + 31) & ~size_t(31); }
+// grid of a persistent kernel (one CTA per SM, each looping over tiles)
+inline int persistent_grid(int64_t n_tiles) {
+  static const int sms = []() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  return (int)(n_tiles < sms ? (n_tiles > 0 ? n_tiles : 1) : sms);
+}
 inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }   // node-blocked tables (tile_engine.cuh: blk_off)
 
 size_t carve(Tables& tb, float* base, int64_t N, int64_t E) {
@@ -953,7 +962,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       static const bool nb16 = []() { const char* e = getenv("MDB_TC_NB16"); return e == nullptr || e[0] != '0'; }();
       if (nb16) {
         LAUNCH(MDB_K_tc_nodeblock, st,
-               (tc_nodeblock_fwd16_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, NB16_THREADS, SMEM_TC_NB16, st>>>(ta)));
+               (tc_nodeblock_fwd16_kernel<<<persistent_grid((E + tc::ROWS - 1) / tc::ROWS), NB16_THREADS, SMEM_TC_NB16, st>>>(ta)));
       } else {
         LAUNCH(MDB_K_tc_nodeblock, st,
                (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));

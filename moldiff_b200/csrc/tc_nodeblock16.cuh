@@ -14,8 +14,16 @@
 #pragma once
 #include "tc_pipe.cuh"
 
+// phase stamps of the persistent kernels are indexed by tile, not by CTA
+#undef TC_STAMP
+#define TC_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)tile * 32 + (i)] = clock64(); } while (0)
+
 constexpr int NB16_NRW = 16;
 constexpr int NB16_THREADS = (NB16_NRW + 4) * 32;   // 640: 4 row warpgroups + {producer, MMA, 2 idle warps}
+#ifndef MDB_NB16_SLICED
+#define MDB_NB16_SLICED 1   // 1: publish the A planes in 4 K-slices (MMA overlaps the remaining stores); 0: one publication
+#endif
+constexpr int NB16_PARTS = MDB_NB16_SLICED ? 4 : 0;
 constexpr int NB16_NS = 3;                           // weight stages (48 KB): leaves room for the 4-way stat buffer
 // smem: E planes | X planes | weight stages | pipe barriers (128 B) | LN stat [4][128] float2 | ls [128] int | vecs [8][256]
 constexpr size_t NB16_VEC_OFF = 2 * (size_t)tc::ROWS * C * 2 + 2 * (size_t)tc::ROWS * D * 2 + NB16_NS * tc::STAGE_SLOT
@@ -89,28 +97,15 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   float* out_tile = reinterpret_cast<float*>(smem_raw);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * tc::ROWS;
   const Tables& tb = a.tb;
-  TC_STAMP(0);
+  const int n_tiles = (a.n_edges + tc::ROWS - 1) / tc::ROWS;
   Pipe16 p;
   tc::pipe_init_split<NB16_NRW, IS_ROW, NB16_NS>(p, ps, stages);
-  if (a.dbg) p.dbg = a.dbg + (size_t)blockIdx.x * 32;
   if (warp == NB16_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
   const int row = (warp & 3) * 32 + lane;
   const int part = (warp >> 2) & 3;
   const int pc = part * 64;                   // first column of this thread's quarter
-  int my_r = -1;
-  float e16[16];                              // this thread's 16 columns of the e tile: in flight across the set-up barrier
   if (IS_ROW) {
-    const int q = q0 + row;
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q < a.n_edges) x = *reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C + part * 16 + i);
-      e16[i] = x.x; e16[i + 1] = x.y; e16[i + 2] = x.z; e16[i + 3] = x.w;
-    }
-    if (q < a.n_edges) { my_r = a.right[q]; if (part == 0) ls[row] = a.left[q]; }
-    else if (part == 0) ls[row] = -1;
     const int vj = tid >> 6;                    // 64 threads per vector
     int so = a.off.o[MDB_S_NB_EN1_B];
     if (vj == 1) so = a.off.o[MDB_S_NB_EN1_G];
@@ -127,6 +122,27 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   tc::fence_after_sync();
   const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t A0 = lane_base + pc, A1 = lane_base + 256 + pc;     // this thread's part of the two accumulators
+
+  // Persistent CTA: TMEM, barriers and the parameter vectors are set up once; the pipeline counters and mbarrier phases
+  // simply keep running across tiles, and the producer prefetches the next tile's first weight stages during the tail.
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int q0 = tile * tc::ROWS;
+  TC_STAMP(0);
+  if (a.dbg) p.dbg = a.dbg + (size_t)tile * 32;
+  int my_r = -1;
+  float e16[16];                              // this thread's 16 columns of the e tile
+  if (IS_ROW) {
+    const int q = q0 + row;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < a.n_edges) x = *reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C + part * 16 + i);
+      e16[i] = x.x; e16[i + 1] = x.y; e16[i + 2] = x.z; e16[i + 3] = x.w;
+    }
+    if (q < a.n_edges) { my_r = a.right[q]; if (part == 0) ls[row] = a.left[q]; }
+    else if (part == 0) ls[row] = -1;
+  }
   const int rr = my_r < 0 ? 0 : my_r;
   TC_STAMP(1);
 
@@ -160,12 +176,13 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
         x[i] = fmaxf((x[i] + v_en1_b[k] - ms.x) * ms.y * v_en1_g[k] + v_en1_be[k], 0.f);
       }
       store_a16(x_hi, x_lo, row, pc + c * 16, x);
-      tc::rows_publish_group(p, c);
+      if (MDB_NB16_SLICED) tc::rows_publish_group(p, c);
     }
+    if (!MDB_NB16_SLICED) tc::rows_publish(p);
     TC_STAMP(7);
   }
   // G2: edge_net.net.3 -> A0 ; m = he * node_net(x)[col]                           graph.py:43
-  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_EN2), 0, false, true, true);
+  tc::gemm<D, D, NB16_NS, NB16_PARTS>(p, x_hi, x_lo, TCW_(NB_EN2), 0, false, true, true);
   if (IS_ROW) {
     const float* hn = tb.hnb + blk_off(rr, pc / 4);     // node-blocked copy: ~4 lines per warp load instead of 32
     float hv[64];                                // gathered node_net(x)[col] row part: requested BEFORE the accumulator wait
@@ -183,12 +200,13 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = (x[i] + v_en2_b[pc + c * 16 + i]) * hv[c * 16 + i];
       store_a16(x_hi, x_lo, row, pc + c * 16, x);
-      tc::rows_publish_group(p, c);
+      if (MDB_NB16_SLICED) tc::rows_publish_group(p, c);
     }
+    if (!MDB_NB16_SLICED) tc::rows_publish(p);
     TC_STAMP(8);
   }
   // G3: msg_net -> A1 (stays in TMEM) ; G4: gate.net.0 edge columns -> A0          graph.py:43,46
-  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_MSG), 256, false, true, false);
+  tc::gemm<D, D, NB16_NS, NB16_PARTS>(p, x_hi, x_lo, TCW_(NB_MSG), 256, false, true, false);
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), 0, false, false, true);
   if (IS_ROW) {
     const float* gxr = tb.gxb + blk_off(rr, pc / 4);
@@ -270,8 +288,10 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
       }
     }
     if (cur >= 0) atomicAdd(tb.agg + (size_t)cur * D + c, s0);
+    asm volatile("bar.sync 1, 512;" ::: "memory");   // the next tile overwrites ls / the planes the out tile aliases
   }
   TC_STAMP(15);
+  }   // tile loop
   tc::cta_sync();
   if (warp == NB16_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
 }

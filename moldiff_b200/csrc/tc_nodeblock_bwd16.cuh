@@ -23,6 +23,9 @@
 #pragma once
 #include "tc_pipe.cuh"
 
+#undef TC_STAMP
+#define TC_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)tile * 32 + (i)] = clock64(); } while (0)
+
 struct TcNbBwd16Args {
   const float* blob;
   const uint8_t* tc_blob;
@@ -87,9 +90,8 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
               *v_g1_g = vecs + 5 * D, *v_g1_be = vecs + 6 * D, *v_g2_b = vecs + 7 * D;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * tc::ROWS;
   const Tables& tb = a.tb;
-  TC_STAMP(0);
+  const int n_tiles = (a.n_edges + tc::ROWS - 1) / tc::ROWS;
   Pipe16 p;
   tc::pipe_init_split<NB16_NRW, IS_ROW, NB16_NS>(p, ps, stages);
   if (tid == 0) { tc::mbar_init(x_free, 1); tc::mbar_init(x_full, 1); tc::fence_barrier_init(); }
@@ -97,16 +99,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   const int row = (warp & 3) * 32 + lane;
   const int part = (warp >> 2) & 3;
   const int pc = part * 64;
-  const int q = q0 + row;
-  const bool valid = IS_ROW && q < a.n_edges;
-  float e16[16];
   if (IS_ROW) {
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) x = *reinterpret_cast<const float4*>(a.e + (size_t)q * C + part * 16 + i);
-      e16[i] = x.x; e16[i + 1] = x.y; e16[i + 2] = x.z; e16[i + 3] = x.w;
-    }
     const int vj = tid >> 6;                    // 64 threads per parameter vector
     int so = a.off.o[MDB_S_NB_EN1_B];
     if (vj == 1) so = a.off.o[MDB_S_NB_EN1_G];
@@ -118,19 +111,36 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
     if (vj == 7) so = a.off.o[MDB_S_NB_G2_B];
     *reinterpret_cast<float4*>(vecs + tid * 4) = *reinterpret_cast<const float4*>(a.blob + so + (tid & 63) * 4);
   }
-  const int ll = valid ? a.left[q] : 0, rr = valid ? a.right[q] : 0;
   tc::fence_before_sync();
   tc::cta_sync();
   tc::fence_after_sync();
-  TC_STAMP(1);
   const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t A0 = lane_base + pc, A1 = lane_base + 256 + pc;
+
+  // persistent CTA (see tc_nodeblock16.cuh); `it` counts this CTA's tiles: parity of the two X-plane reload barriers
+#pragma unroll 1
+  for (int tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+  const int q0 = tile * tc::ROWS;
+  TC_STAMP(0);
+  const int q = q0 + row;
+  const bool valid = IS_ROW && q < a.n_edges;
+  float e16[16];
+  if (IS_ROW) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) x = *reinterpret_cast<const float4*>(a.e + (size_t)q * C + part * 16 + i);
+      e16[i] = x.x; e16[i + 1] = x.y; e16[i + 2] = x.z; e16[i + 3] = x.w;
+    }
+  }
+  const int ll = valid ? a.left[q] : 0, rr = valid ? a.right[q] : 0;
+  TC_STAMP(1);
   const float* hn = tb.hnb + blk_off(rr, pc / 4);      // node-blocked tables (tile_engine.cuh): coalesced gathers / REDs
   const float* gxr = tb.gxb + blk_off(rr, pc / 4);
   // he scratch, tile-blocked so that a warp instruction (32 consecutive rows, one 16-byte piece each) touches 4 lines
   // instead of 32: [tile][16-byte column piece 0..63][row 0..127][4 floats]
-  float* he_scr = a.scr_he + (size_t)blockIdx.x * tc::ROWS * D + (size_t)(pc / 4) * tc::ROWS * 4 + row * 4;
-  uint8_t* dm_scr = a.scr_dm + (size_t)blockIdx.x * 2 * PLANE256_BYTES;
+  float* he_scr = a.scr_he + (size_t)tile * tc::ROWS * D + (size_t)(pc / 4) * tc::ROWS * 4 + row * 4;
+  uint8_t* dm_scr = a.scr_dm + (size_t)tile * 2 * PLANE256_BYTES;
   float2 ms_en1 = make_float2(0.f, 1.f), ms_g1 = make_float2(0.f, 1.f);
   float de16[16];
 
@@ -312,10 +322,10 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   if (!IS_ROW) {
     if (p.role == 2) {
       tc::mma_commit(x_free);                    // arrives when BT_NB_GE has finished reading the X planes
-      tc::mbar_wait(x_full, 0);
+      tc::mbar_wait(x_full, it & 1);
       tc::fence_after_sync();
     } else if (p.role == 1) {
-      tc::mbar_wait(x_free, 0);
+      tc::mbar_wait(x_free, it & 1);
       tc::mbar_arrive_expect_tx(x_full, 2 * PLANE256_BYTES);
       tc::bulk_g2s(x_hi, dm_scr, PLANE256_BYTES, x_full);
       tc::bulk_g2s(x_lo, dm_scr + PLANE256_BYTES, PLANE256_BYTES, x_full);
@@ -412,6 +422,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
     tc::fence_before_sync();
   }
   TC_STAMP(19);
+  }   // tile loop
   tc::cta_sync();
   if (warp == NB16_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
 }
