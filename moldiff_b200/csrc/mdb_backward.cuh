@@ -741,6 +741,15 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
   CUDA_TRY(cudaMemsetAsync(sv.dg, 0, (size_t)E * G * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(d_pos, 0, (size_t)N * 3 * sizeof(float), st));
 
+  // Scatter accumulators of block L-1 (every later block's are re-zeroed by bwd_node_kernel after it consumed them).  They
+  // are left zero by a completed backward, but a FRESH workspace (torch.empty, recycled allocator blocks) is not: zero them
+  // here instead of relying on it.
+  CUDA_TRY(cudaMemsetAsync(sv.dul, 0, NC * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dur, 0, NC * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dgx, 0, (size_t)pad64(N) * D * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dhn, 0, (size_t)pad64(N) * D * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dnl, 0, (size_t)2 * N * 128 * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dgn, 0, (size_t)2 * N * 32 * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(sv.gamax, 0, 32 * sizeof(float), st));
   const size_t n_dl = (size_t)plan->n_half * net->num_edge_types;
   if (n_dl > 0) {

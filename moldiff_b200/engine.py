@@ -258,7 +258,8 @@ class GraphPlan:
         ws = self._workspace.get(key)
         if ws is None:
             nbytes = load_library().mdb_workspace_bytes(self.n_nodes, self.n_edges, key[0], key[1])
-            ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            # zero-filled once: several accumulators in the workspace are "left zero by the previous call"
+            ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
             self._workspace[key] = ws
         return ws
 

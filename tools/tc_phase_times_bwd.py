@@ -34,8 +34,8 @@ lib.mdb_debug_set_buffer(None)
 t = buf.view(tiles, 32).cpu().numpy().astype(np.int64)
 names = ["set-up", "e tile -> planes",
          "wait EN1", "epi LN(en1)", "wait EN2", "epi he*hn (+he scratch)", "wait MSG+GE", "epi LN(g1)+gx", "wait G2",
-         "epi dout: dgt->planes, dmsg->scratch", "wait BT_G2+GE", "epi LN bwd(g1) + RED dgx", "wait BT_GE", "de -> regs",
-         "wait reload+BT_MSG", "epi dhn RED + d he", "wait BT_EN2+EN1", "epi LN bwd(en1)", "wait BT_EN1", "epi de out"]
+         "epi dout: dgt->planes, dmsg->scratch", "wait BT_G2+GE", "epi LN bwd(g1) + RED dgx", "wait BT_GE",
+         "de -> regs, wait reload+BT_MSG", "epi dhn RED + d he", "wait BT_EN2+EN1", "epi LN bwd(en1)", "wait BT_EN1", "epi de out"]
 NS = len(names)
 d = t[:, 1:NS + 1] - t[:, 0:NS]
 print(f"tiles {tiles}; per-tile cycles mean / median / p90 (last launch = block 0 of the bond predictor backward)")
