@@ -256,6 +256,8 @@ int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int3
 /* Debug: device int64 buffer [n_tiles][32] that tc_nodeblock_fwd_kernel fills with clock64() phase stamps of its row
  * thread 0 (NULL = off, the default).  tools/tc_phase_times.py prints the per-phase breakdown. */
 void mdb_debug_set_buffer(void* device_i64_buffer);
+/* Which kernel writes the stamps: 0 = NodeBlock forward (default), 1 = NodeBlock backward, 2 = BondFFN forward. */
+void mdb_debug_select(int32_t kernel);
 
 /* Diagnostics. */
 const char* mdb_last_error(void);

@@ -805,7 +805,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
         ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
         for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
         ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
-        ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
+        ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_sel == 1 ? g_dbg_stamps : nullptr;
         ta.scr_he = sv.scr_he; ta.scr_dm = reinterpret_cast<uint8_t*>(sv.scr_dm);
         LAUNCH(MDB_K_tc_nodeblock_bwd, st,
                (tc_nodeblock_bwd16_kernel<<<persistent_grid((E + tc::ROWS - 1) / tc::ROWS), NB16_THREADS, SMEM_TC_NB_BWD16, st>>>(ta)));
@@ -815,7 +815,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
         ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
         for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
         ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
-        ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_stamps;
+        ta.e = ea.e; ta.dagg = sv.dagg; ta.dgx = sv.dgx; ta.dhn = sv.dhn; ta.de = sv.de; ta.dbg = g_dbg_sel == 1 ? g_dbg_stamps : nullptr;
         fill_nb_vecs(ta.v, net->blob_host, ea.off);
         LAUNCH(MDB_K_tc_nodeblock_bwd, st,
                (tc_nodeblock_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, tc::RB_THREADS, SMEM_TC_NB_BWD, st>>>(ta)));

@@ -687,6 +687,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 thread_local char g_err[512] = "";
 int64_t g_launches = 0;
 bool g_profiling = false;
+int g_dbg_sel = 0;                    // which kernel fills the stamp buffer: 0 nodeblock fwd, 1 nodeblock bwd, 2 bondffn fwd
 long long* g_dbg_stamps = nullptr;   // optional device buffer for in-kernel clock64 phase stamps (mdb_debug_set_buffer)
 struct ProfRec { int cls; cudaEvent_t a, b; };
 std::vector<ProfRec> g_prof;
@@ -946,6 +947,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       fa.left = plan->left; fa.right = plan->right; fa.n_nodes = N; fa.n_edges = E;
       fa.pos = pos_cur; fa.rbf_lo = net->rbf_start; fa.rbf_hi = net->rbf_stop; fa.ebuf = ea.ebuf; fa.sl = ea.sl;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
+      fa.dbg = g_dbg_sel == 2 ? g_dbg_stamps : nullptr;
       LAUNCH(MDB_K_tc_bondffn, st,
              (tc_bondffn_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
     } else if (E > 0) {
@@ -957,7 +959,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       ta.blob = net->blob; ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); ta.off = ea.off; ta.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E; ta.ebuf = ea.ebuf;
-      ta.dbg = g_dbg_stamps;
+      ta.dbg = g_dbg_sel == 0 ? g_dbg_stamps : nullptr;
       fill_nb_vecs(ta.v, net->blob_host, ea.off);
       static const bool nb16 = []() { const char* e = getenv("MDB_TC_NB16"); return e == nullptr || e[0] != '0'; }();
       if (nb16) {
@@ -1116,6 +1118,7 @@ int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int3
 }
 
 void mdb_debug_set_buffer(void* device_i64_buffer) { g_dbg_stamps = reinterpret_cast<long long*>(device_i64_buffer); }
+void mdb_debug_select(int32_t kernel) { g_dbg_sel = kernel; }
 
 void mdb_profile_begin(void) {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

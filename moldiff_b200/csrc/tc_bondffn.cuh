@@ -24,7 +24,9 @@ struct TcFfnArgs {
   float* ebuf;             // [E][64] out: e
   float* sl;               // [2][N][64] SL, SR accumulators (pre-zeroed)
   FfnVecs v;
+  long long* dbg;          // optional [grid][32] clock64 stamps of row thread 0 (tools/tc_phase_times.py --ffn)
 };
+#define FFN_STAMP(i) do { if (a.dbg && tid == 0) a.dbg[(size_t)blockIdx.x * 32 + (i)] = clock64(); } while (0)
 
 template <int NC>
 __device__ __forceinline__ void load_cols_tm(uint32_t taddr, float (&v)[NC]) {
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
   float* o_tile = reinterpret_cast<float*>(a_hi);            // [128][FFN_O_LD] fp32 at the very end (A planes dead)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  FFN_STAMP(0);
   const int q0 = blockIdx.x * tc::ROWS;
   const Tables& tb = a.tb;
   tc::Pipe p;
@@ -133,11 +136,13 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
     }
     tc::store_a<KI, 8>(a_hi, a_lo, row, C + half * 8, g);
     tc::rows_publish(p);
+    FFN_STAMP(1);
   }
   // G0: e = edge_embs(cat)                                                        graph.py:354-357
   tc::gemm<KI, C>(p, a_hi, a_lo, TCW_(EE), 0, false, true, true);
   if (p.role == 0) {
     tc::rows_wait_acc(p);
+    FFN_STAMP(2);
     float v[32];
     tc::tmem_ld32(lane_base + half * 32, v);
 #pragma unroll
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
     }
     tc::store_a<C, 32>(e_hi, e_lo, row, half * 32, v);
     tc::rows_publish(p);
+    FFN_STAMP(3);
   }
 #pragma unroll 1
   for (int side = 0; side < 2; ++side) {
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
       float nlv[64], gnv[16];
       gather_n<64>(nl, nlv); gather_n<16>(gn, gnv);
       tc::rows_wait_acc(p);
+      FFN_STAMP(4 + side * 8);
       {
         float v[64];
         load_cols_tm<64>(lane_base + half * 64, v);
@@ -184,6 +191,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
         tc::store_a<32, 16>(g_hi, g_lo, row, half * 16, g);
       }
       tc::rows_publish(p);
+      FFN_STAMP(5 + side * 8);
     }
     // inter_module.net.0 -> D[0:128] ; gate.net.3 -> D[128:192]                   graph.py:137,139
     tc::gemm<128, 128>(p, a_hi, a_lo, w_i1, 0, false, true, false);
@@ -191,6 +199,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
     float sgg[32];
     if (p.role == 0) {
       tc::rows_wait_acc(p);
+      FFN_STAMP(6 + side * 8);
       {
         float v[64];
         load_cols_tm<64>(lane_base + half * 64, v);
@@ -203,11 +212,13 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
 #pragma unroll
       for (int i = 0; i < 32; ++i) sgg[i] = tc::fast_sigmoid(sgg[i] + sv.g2_b[half * 32 + i]);
       tc::rows_publish(p);
+      FFN_STAMP(7 + side * 8);
     }
     // inter_module.net.3 -> D[0:64]                                                graph.py:137
     tc::gemm<128, C>(p, a_hi, a_lo, w_i2, 0, false, true, true);
     if (p.role == 0) {
       tc::rows_wait_acc(p);
+      FFN_STAMP(8 + side * 8);
       float o[32];
       tc::tmem_ld32(lane_base + half * 32, o);
 #pragma unroll
@@ -240,6 +251,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
         }
         if (cur >= 0) atomicAdd(sr + (size_t)cur * C + c, s);
       }
+      FFN_STAMP(9 + side * 8);
       if (side == 0) tc::rows_publish(p);     // accumulator drained: the right FFN's first GEMM may overwrite it
     }
   }

@@ -37,12 +37,13 @@ struct PipeT {
   uint32_t n_ready;     // a_ready phases consumed (MMA thread)
   int role;             // 0 = row thread, 1 = producer thread, 2 = MMA thread, 3 = idle lane
   long long* dbg;       // optional clock64 stamps of the MMA thread (phase-timing tool), else nullptr
+  uint32_t slot_bytes;  // stride of the weight-stage ring (STAGE_SLOT unless the kernel's widest N is < 256)
 };
 using Pipe = PipeT<NSTAGE>;
 
 template <int NRW = 4, int NS = NSTAGE>   // NRW row warps: 4 = one thread per row, 8 / 16 = two / four threads per row
 __device__ __forceinline__ void pipe_init(PipeT<NS>& p, PipeSmemT<NS>* s, uint8_t* stages) {
-  p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0; p.dbg = nullptr;
+  p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0; p.dbg = nullptr; p.slot_bytes = STAGE_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   p.role = warp < NRW ? 0 : (lane == 0 ? (warp == NRW ? 1 : 2) : 3);
   if (threadIdx.x == 0) {
@@ -155,7 +156,7 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->empty[slot], ph ^ 1);
       mbar_arrive_expect_tx(&p.s->full[slot], WS::STAGE_BYTES);
-      bulk_g2s(p.stages + slot * STAGE_SLOT, w_img + (size_t)kstep_of<NS, NPARTS>(s) * WS::STAGE_BYTES, WS::STAGE_BYTES,
+      bulk_g2s(p.stages + slot * p.slot_bytes, w_img + (size_t)kstep_of<NS, NPARTS>(s) * WS::STAGE_BYTES, WS::STAGE_BYTES,
                &p.s->full[slot]);
     }
   } else if (p.role == 2) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->full[slot], ph);
       fence_after_sync();
-      const uint32_t bhi = smem_u32(p.stages + slot * STAGE_SLOT), blo = bhi + WS::PLANE_BYTES;
+      const uint32_t bhi = smem_u32(p.stages + slot * p.slot_bytes), blo = bhi + WS::PLANE_BYTES;
       const uint32_t ks = (uint32_t)kstep_of<NS, NPARTS>(s);
       const uint64_t da_hi = make_smem_desc(ahi + ks * 256, 128, SBO_A);
       const uint64_t da_lo = make_smem_desc(alo + ks * 256, 128, SBO_A);

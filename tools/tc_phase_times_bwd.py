@@ -27,6 +27,7 @@ tiles = (E + 127) // 128
 buf = torch.zeros(tiles * 32, dtype=torch.int64, device=dev)
 lib = engine.load_library()
 lib.mdb_debug_set_buffer.argtypes = [C.c_void_p]
+lib.mdb_debug_select(1)
 lib.mdb_debug_set_buffer(buf.data_ptr())
 model.sample_step(st, 499, bond_predictor=bond, guidance=g)
 torch.cuda.synchronize()

@@ -1,4 +1,4 @@
-"""GPU tool: per-phase cycle breakdown of tc_nodeblock_fwd_kernel from in-kernel clock64 stamps (config 2 graph)."""
+"""GPU tool: per-phase cycle breakdown of tc_bondffn_fwd_kernel (clock64 stamps of row thread 0; config 2 graph)."""
 import ctypes as C
 import os
 import sys
@@ -24,23 +24,19 @@ tiles = (E + 127) // 128
 buf = torch.zeros(tiles * 32, dtype=torch.int64, device=dev)
 lib = engine.load_library()
 lib.mdb_debug_set_buffer.argtypes = [C.c_void_p]
-lib.mdb_debug_select(0)
+lib.mdb_debug_select(2)
 lib.mdb_debug_set_buffer(buf.data_ptr())
 model.sample_step(st, 499)
 torch.cuda.synchronize()
 lib.mdb_debug_set_buffer(None)
 t = buf.view(tiles, 32).cpu().numpy().astype(np.int64)
-order = [0, 1, 6, 2, 7, 3, 8, 4, 9, 5, 15]
-names = ["setup(alloc,barriers,sync)", "e tile -> E planes", "wait G1 (64x256)", "epilogue 1 (LN)", "wait G2 (256x256)",
-         "epilogue 2 (*hn)", "wait G3+G4", "epilogue 3 (LN+gx)", "wait G5 (256x256)", "epilogue 4 + reduction"]
+order = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17]
+names = ["set-up + input planes (h_edge, rbf)", "wait EE (80x64)", "epi e -> ebuf, E planes",
+         "L: wait BL+GB", "L: epi *nl, gate LN", "L: wait I1+G2", "L: epi LN(128), sigmoid", "L: wait I2", "L: epi out, RED SL[r]",
+         "R: wait BL+GB", "R: epi *nl, gate LN", "R: wait I1+G2", "R: epi LN(128), sigmoid", "R: wait I2", "R: epi out, run-reduce SR"]
 d = np.stack([t[:, order[i + 1]] - t[:, order[i]] for i in range(len(order) - 1)], 1)
 print(f"tiles {tiles}; per-tile cycles (mean / median / p90), last block's kernel only")
 for i, n in enumerate(names):
-    print(f"  {n:32s} {d[:, i].mean():9.0f} {np.median(d[:, i]):9.0f} {np.percentile(d[:, i], 90):9.0f}")
-tot = t[:, 15] - t[:, 0]
-print(f"  {'total':32s} {tot.mean():9.0f} {np.median(tot):9.0f} {np.percentile(tot, 90):9.0f}")
-
-# MMA-thread stamps of the LAST sliced GEMM (G5): a_ready group waits and the final commit, relative to the start of epilogue 3
-rel = lambda c: (t[:, c] - t[:, 4])
-print("G5 (sliced): rows start epi3 = 0; rows end epi3 %.0f; MMA saw group 0/1/2/3 at %.0f / %.0f / %.0f / %.0f; MMA issued last commit %.0f; rows saw done %.0f"
-      % (rel(9).mean(), rel(16).mean(), rel(17).mean(), rel(18).mean(), rel(19).mean(), rel(20).mean(), rel(5).mean()))
+    print(f"  {n:38s} {d[:, i].mean():9.0f} {np.median(d[:, i]):9.0f} {np.percentile(d[:, i], 90):9.0f}")
+tot = t[:, 17] - t[:, 0]
+print(f"  {'total':38s} {tot.mean():9.0f} {np.median(tot):9.0f} {np.percentile(tot, 90):9.0f}")
