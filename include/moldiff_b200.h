@@ -214,7 +214,7 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
   X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
-  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition)
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition) X(graph_build)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,
@@ -240,6 +240,18 @@ int mdb_transition_step(int32_t n_nodes, int32_t n_half, int32_t kn, int32_t ke,
                         const float* qn_stepT, float* log_node_out, float* h_node_out, const float* pred_half,
                         const float* log_half, const float* u_half, const float* qe_cum, const float* qe_stepT,
                         float* log_half_out, float* h_edge_out, int64_t* half_type_out, void* stream);
+
+/*
+ * Edge builders over atom positions (torch_geometric.nn.radius_graph / knn_graph, imported by models/graph.py:6 and
+ * reached only from dead code there -- SURVEY.md 8f N4).  Nodes of one graph must be contiguous: seg_lo[i] / seg_hi[i]
+ * are the first / one-past-last node index of node i's graph.  Output: counts[i] neighbours of centre i in
+ * neighbors[i * max .. ) (max = max_num_neighbors or k): radius -- every j with |pos_j - pos_i| < radius in index
+ * order, truncated at max_num_neighbors; knn -- the k nearest, ascending distance, ties by index.  loop != 0 keeps j == i.
+ */
+int mdb_radius_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, const int32_t* seg_hi, float radius,
+                     int32_t loop, int32_t max_num_neighbors, int32_t* counts, int32_t* neighbors, void* stream);
+int mdb_knn_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, const int32_t* seg_hi, int32_t k, int32_t loop,
+                  int32_t* counts, int32_t* neighbors, void* stream);
 
 /* Profiling: between begin and end every kernel launch of this library is bracketed by CUDA events on
  * its own stream; end synchronises those events and returns summed milliseconds / launch counts per

@@ -1016,6 +1016,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 #include "mdb_backward.cuh"
 #include "tc_selftest.cuh"
 #include "mdb_transition.cuh"
+#include "mdb_graph_build.cuh"
 
 }  // namespace
 
@@ -1080,6 +1081,29 @@ int mdb_transition_step(int32_t n_nodes, int32_t n_half, int32_t kn, int32_t ke,
   } else {
     LAUNCH(MDB_K_transition, st, (transition_step_kernel<0, 0><<<(total + 255) / 256, 256, 0, st>>>(a)));
   }
+  return MDB_OK;
+}
+
+int mdb_radius_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, const int32_t* seg_hi, float radius,
+                     int32_t loop, int32_t max_num_neighbors, int32_t* counts, int32_t* neighbors, void* stream) {
+  if (n_nodes < 0 || max_num_neighbors < 1 || !(radius > 0.f)) return fail(MDB_EINVAL, "mdb_radius_graph: bad arguments%s");
+  if (n_nodes == 0) return MDB_OK;
+  if (!pos || !seg_lo || !seg_hi || !counts || !neighbors) return fail(MDB_EINVAL, "null argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH(MDB_K_graph_build, st,
+         (radius_graph_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(n_nodes, pos, seg_lo, seg_hi, radius * radius, loop,
+                                                                    max_num_neighbors, counts, neighbors)));
+  return MDB_OK;
+}
+
+int mdb_knn_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, const int32_t* seg_hi, int32_t k, int32_t loop,
+                  int32_t* counts, int32_t* neighbors, void* stream) {
+  if (n_nodes < 0 || k < 1 || k > KNN_MAX_K) return fail(MDB_EINVAL, "mdb_knn_graph: k must be in 1..32%s");
+  if (n_nodes == 0) return MDB_OK;
+  if (!pos || !seg_lo || !seg_hi || !counts || !neighbors) return fail(MDB_EINVAL, "null argument%s");
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH(MDB_K_graph_build, st,
+         (knn_graph_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(n_nodes, pos, seg_lo, seg_hi, k, loop, counts, neighbors)));
   return MDB_OK;
 }
 

@@ -90,6 +90,10 @@ def load_library():
         lib.mdb_bondpred_backward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 8 + [sz, vp]
         lib.mdb_tc_selftest.restype = C.c_int
         lib.mdb_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        lib.mdb_radius_graph.restype = C.c_int
+        lib.mdb_radius_graph.argtypes = [i32, vp, vp, vp, f32, i32, i32, vp, vp, vp]
+        lib.mdb_knn_graph.restype = C.c_int
+        lib.mdb_knn_graph.argtypes = [i32, vp, vp, vp, i32, i32, vp, vp, vp]
         lib.mdb_transition_step.restype = C.c_int
         lib.mdb_transition_step.argtypes = [i32, i32, i32, i32] + [vp] * 26
         lib.mdb_profile_begin.restype = None
