@@ -214,7 +214,7 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
   X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
-  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition) X(graph_build)
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition) X(graph_build) X(decode_rows)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,
@@ -240,6 +240,15 @@ int mdb_transition_step(int32_t n_nodes, int32_t n_half, int32_t kn, int32_t ke,
                         const float* qn_stepT, float* log_node_out, float* h_node_out, const float* pred_half,
                         const float* log_half, const float* u_half, const float* qe_cum, const float* qe_stepT,
                         float* log_half_out, float* h_edge_out, int64_t* half_type_out, void* stream);
+
+/*
+ * mdb_decode_rows <- the softmax / argmax / max arithmetic of FeaturizeMol.decode_output (utils/transforms.py:76-96) for a
+ * whole batch: node_type[i] = argmax_k pred_node[i,k], node_prob[i] = softmax(pred_node[i])[node_type[i]], same for the
+ * half-edges.  uint8 classes, fp32 probabilities.  The caller (moldiff_b200/decode.py) does the index bookkeeping
+ * (masked atoms, bond filtering, per-molecule split of utils/sample.py:4-30) on the host.
+ */
+int mdb_decode_rows(int32_t n_nodes, int32_t kn, const float* pred_node, int32_t n_half, int32_t ke, const float* pred_half,
+                    uint8_t* node_type, float* node_prob, uint8_t* half_type, float* half_prob, void* stream);
 
 /*
  * Edge builders over atom positions (torch_geometric.nn.radius_graph / knn_graph, imported by models/graph.py:6 and

@@ -1017,6 +1017,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 #include "tc_selftest.cuh"
 #include "mdb_transition.cuh"
 #include "mdb_graph_build.cuh"
+#include "mdb_decode.cuh"
 
 }  // namespace
 
@@ -1081,6 +1082,17 @@ int mdb_transition_step(int32_t n_nodes, int32_t n_half, int32_t kn, int32_t ke,
   } else {
     LAUNCH(MDB_K_transition, st, (transition_step_kernel<0, 0><<<(total + 255) / 256, 256, 0, st>>>(a)));
   }
+  return MDB_OK;
+}
+
+int mdb_decode_rows(int32_t n_nodes, int32_t kn, const float* pred_node, int32_t n_half, int32_t ke, const float* pred_half,
+                    uint8_t* node_type, float* node_prob, uint8_t* half_type, float* half_prob, void* stream) {
+  if (n_nodes < 0 || n_half < 0 || kn < 1 || ke < 1 || kn > 255 || ke > 255) return fail(MDB_EINVAL, "mdb_decode_rows: bad sizes%s");
+  if (n_nodes + n_half == 0) return MDB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH(MDB_K_decode_rows, st,
+         (decode_rows_kernel<<<(n_nodes + n_half + 255) / 256, 256, 0, st>>>(n_nodes, kn, pred_node, n_half, ke, pred_half,
+                                                                             node_type, node_prob, half_type, half_prob)));
   return MDB_OK;
 }
 

@@ -90,6 +90,8 @@ def load_library():
         lib.mdb_bondpred_backward.argtypes = [C.POINTER(NetDesc), C.POINTER(Plan)] + [vp] * 8 + [sz, vp]
         lib.mdb_tc_selftest.restype = C.c_int
         lib.mdb_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+        lib.mdb_decode_rows.restype = C.c_int
+        lib.mdb_decode_rows.argtypes = [i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.mdb_radius_graph.restype = C.c_int
         lib.mdb_radius_graph.argtypes = [i32, vp, vp, vp, f32, i32, i32, vp, vp, vp]
         lib.mdb_knn_graph.restype = C.c_int
