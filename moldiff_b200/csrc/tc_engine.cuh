@@ -105,6 +105,47 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged issue: every lane of the MMA warp executes these; ONE elected lane (elect.sync, always the same lane for
+// a full mask) issues.  Keeping the C++ control flow converged lets ptxas hold the descriptors in uniform registers
+// instead of wrapping each UTCHMMA in an R2UR + ELECT/BRA.U.ANY uniformisation loop.
+template <bool ACC_IMM, bool ACC = true>
+__device__ __forceinline__ void mma_f16_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate = 1u) {
+  if constexpr (ACC_IMM) {
+    asm volatile(
+        "{\n\t.reg .pred e, p;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred e, p;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// same with the accumulate flag as a compile-time immediate (no setp per MMA in the issue thread's unrolled K loop)
+template <bool ACC>
+__device__ __forceinline__ void mma_f16_ss_imm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
 // mbarrier arrives when all tcgen05.mma issued so far by this thread have completed (implies before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

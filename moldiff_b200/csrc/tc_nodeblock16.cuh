@@ -296,7 +296,7 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   if (warp == NB16_NRW) { __syncwarp(); tc::tmem_dealloc<512>(ps->tmem_base); }
 }
 
-// 640 threads compile to 96 registers; the producer/MMA warpgroup keeps 32, the four row warpgroups get 112.
+// 640 threads compile to 96 registers; the producer/MMA warpgroup keeps 32, the four row warpgroups get 112 (inc and dec must balance inside the CTA pool: 512 x 16 = 128 x 64 -- an unbalanced inc blocks forever).
 __global__ void __launch_bounds__(NB16_THREADS, 1) tc_nodeblock_fwd16_kernel(const __grid_constant__ TcNbArgs a) {
   if (threadIdx.x < NB16_NRW * 32) {
     tc::reg_alloc<112>();

@@ -321,7 +321,7 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   // ---- d msg planes come back from the scratch slab (no row-thread work) ---------------------------------------
   if (!IS_ROW) {
     if (p.role == 2) {
-      tc::mma_commit(x_free);                    // arrives when BT_NB_GE has finished reading the X planes
+      tc::mma_commit_elect(x_free);              // arrives when BT_NB_GE has finished reading the X planes
       tc::mbar_wait(x_full, it & 1);
       tc::fence_after_sync();
     } else if (p.role == 1) {

@@ -45,7 +45,8 @@ template <int NRW = 4, int NS = NSTAGE>   // NRW row warps: 4 = one thread per r
 __device__ __forceinline__ void pipe_init(PipeT<NS>& p, PipeSmemT<NS>* s, uint8_t* stages) {
   p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0; p.dbg = nullptr; p.slot_bytes = STAGE_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  p.role = warp < NRW ? 0 : (lane == 0 ? (warp == NRW ? 1 : 2) : 3);
+  // the MMA warp runs its loop CONVERGED (all 32 lanes, one elected issuer): descriptors stay warp-uniform
+  p.role = warp < NRW ? 0 : (warp == NRW ? (lane == 0 ? 1 : 3) : (warp == NRW + 1 ? 2 : 3));
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&s->full[i], 1); mbar_init(&s->empty[i], 1); }
     mbar_init(&s->done, 1);
@@ -70,7 +71,7 @@ __device__ __forceinline__ void pipe_init_split(PipeT<NS>& p, PipeSmemT<NS>* s, 
   pipe_init<NRW, NS>(p, s, stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if constexpr (IS_ROW) p.role = 0;
-  else p.role = lane == 0 ? (warp == NRW ? 1 : (warp == NRW + 1 ? 2 : 3)) : 3;
+  else p.role = warp == NRW ? (lane == 0 ? 1 : 3) : (warp == NRW + 1 ? 2 : 3);
 }
 
 // Row threads: "my part of the A planes is written and I no longer read the accumulator".
@@ -171,31 +172,36 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const
     constexpr uint32_t idesc = make_idesc_f16(ROWS, N, OPERAND_FMT, OPERAND_FMT);
     constexpr uint32_t SBO_A = (K / 8) * 128;
     const uint32_t d_tmem = p.s->tmem_base + d_col;
-    const uint32_t ahi = smem_u32(a_hi), alo = smem_u32(a_lo);
+    // The issuing thread is the pipe's critical path for small-N GEMMs (an N = 64 MMA executes in 32 cycles): keep its K
+    // loop lean -- descriptors are built once, a K step / ring slot only adds to their 14-bit address field (units of 16 B;
+    // shared memory is < 256 KB, so no carry), the accumulate flag of every MMA but the first is an immediate.
+    const uint64_t da_hi0 = make_smem_desc(smem_u32(a_hi), 128, SBO_A);
+    const uint64_t da_lo0 = make_smem_desc(smem_u32(a_lo), 128, SBO_A);
+    const uint64_t db0 = make_smem_desc(smem_u32(p.stages), 128, WS::SBO);
+    const uint32_t slot_units = p.slot_bytes >> 4;
+    const bool leader = (threadIdx.x & 31) == 0;      // all lanes walk the loop and wait; one elected lane issues
+#pragma unroll 1                                      // rolled: a handful of live registers (the warpgroup keeps 32)
     for (int s = 0; s < NS; ++s, ++p.it) {
       if constexpr (NPARTS != 0) {
         if (wait_ready && s % (NS / NGRP) == 0) {
           mbar_wait(&p.s->a_ready[s / (NS / NGRP)], ready_parity);
           fence_after_sync();
-          if (p.dbg) p.dbg[16 + s / (NS / NGRP)] = clock64();
+          if (p.dbg && leader) p.dbg[16 + s / (NS / NGRP)] = clock64();
         }
       }
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->full[slot], ph);
       fence_after_sync();
-      const uint32_t bhi = smem_u32(p.stages + slot * p.slot_bytes), blo = bhi + WS::PLANE_BYTES;
       const uint32_t ks = (uint32_t)kstep_of<NS, NPARTS>(s);
-      const uint64_t da_hi = make_smem_desc(ahi + ks * 256, 128, SBO_A);
-      const uint64_t da_lo = make_smem_desc(alo + ks * 256, 128, SBO_A);
-      const uint64_t db_hi = make_smem_desc(bhi, 128, WS::SBO);
-      const uint64_t db_lo = make_smem_desc(blo, 128, WS::SBO);
-      mma_bf16_ss(d_tmem, da_hi, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
-      mma_bf16_ss(d_tmem, da_lo, db_hi, idesc, 1u);
-      mma_bf16_ss(d_tmem, da_hi, db_lo, idesc, 1u);
-      mma_commit(&p.s->empty[slot]);
+      const uint64_t da_hi = da_hi0 + ks * 16u, da_lo = da_lo0 + ks * 16u;   // + ks * 256 bytes
+      const uint64_t db_hi = db0 + slot * slot_units, db_lo = db_hi + (WS::PLANE_BYTES >> 4);
+      mma_f16_ss_elect<false>(d_tmem, da_hi, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
+      mma_f16_ss_elect<true>(d_tmem, da_lo, db_hi, idesc);
+      mma_f16_ss_elect<true>(d_tmem, da_hi, db_lo, idesc);
+      mma_commit_elect(&p.s->empty[slot]);
     }
-    if (signal_done) mma_commit(&p.s->done);
-    if (p.dbg) p.dbg[20] = clock64();
+    if (signal_done) mma_commit_elect(&p.s->done);
+    if (p.dbg && leader) p.dbg[20] = clock64();
   }
 }
 
