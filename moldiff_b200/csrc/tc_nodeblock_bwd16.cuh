@@ -326,9 +326,12 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
       tc::fence_after_sync();
     } else if (p.role == 1) {
       tc::mbar_wait(x_free, it & 1);
-      tc::mbar_arrive_expect_tx(x_full, 2 * PLANE256_BYTES);
-      tc::bulk_g2s(x_hi, dm_scr, PLANE256_BYTES, x_full);
-      tc::bulk_g2s(x_lo, dm_scr + PLANE256_BYTES, PLANE256_BYTES, x_full);
+      if (lane == 0) {
+        tc::mbar_arrive_expect_tx(x_full, 2 * PLANE256_BYTES);
+        tc::bulk_g2s(x_hi, dm_scr, PLANE256_BYTES, x_full);
+        tc::bulk_g2s(x_lo, dm_scr + PLANE256_BYTES, PLANE256_BYTES, x_full);
+      }
+      __syncwarp();
     }
   }
   tc::gemm<D, D>(p, x_hi, x_lo, TCW_(BT_NB_MSG), 256, false, true, true);                  // d m -> A1

@@ -45,8 +45,9 @@ template <int NRW = 4, int NS = NSTAGE>   // NRW row warps: 4 = one thread per r
 __device__ __forceinline__ void pipe_init(PipeT<NS>& p, PipeSmemT<NS>* s, uint8_t* stages) {
   p.s = s; p.stages = stages; p.it = 0; p.n_done = 0; p.n_ready = 0; p.dbg = nullptr; p.slot_bytes = STAGE_SLOT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // the MMA warp runs its loop CONVERGED (all 32 lanes, one elected issuer): descriptors stay warp-uniform
-  p.role = warp < NRW ? 0 : (warp == NRW ? (lane == 0 ? 1 : 3) : (warp == NRW + 1 ? 2 : 3));
+  // the producer and MMA warps run their loops CONVERGED (all 32 lanes, one elected lane acts): no per-instruction
+  // uniformisation loops around the UBLKCP / UTCHMMA issue
+  p.role = warp < NRW ? 0 : (warp == NRW ? 1 : (warp == NRW + 1 ? 2 : 3));
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&s->full[i], 1); mbar_init(&s->empty[i], 1); }
     mbar_init(&s->done, 1);
@@ -71,7 +72,7 @@ __device__ __forceinline__ void pipe_init_split(PipeT<NS>& p, PipeSmemT<NS>* s, 
   pipe_init<NRW, NS>(p, s, stages);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if constexpr (IS_ROW) p.role = 0;
-  else p.role = warp == NRW ? (lane == 0 ? 1 : 3) : (warp == NRW + 1 ? 2 : 3);
+  else p.role = warp == NRW ? 1 : (warp == NRW + 1 ? 2 : 3);
 }
 
 // Row threads: "my part of the A planes is written and I no longer read the accumulator".
@@ -156,9 +157,8 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT>& p, const uint8_t* a_hi, const
     for (int s = 0; s < NS; ++s, ++p.it) {
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
       mbar_wait(&p.s->empty[slot], ph ^ 1);
-      mbar_arrive_expect_tx(&p.s->full[slot], WS::STAGE_BYTES);
-      bulk_g2s(p.stages + slot * p.slot_bytes, w_img + (size_t)kstep_of<NS, NPARTS>(s) * WS::STAGE_BYTES, WS::STAGE_BYTES,
-               &p.s->full[slot]);
+      stage_load_elect(p.stages + slot * p.slot_bytes, w_img + (size_t)kstep_of<NS, NPARTS>(s) * WS::STAGE_BYTES,
+                       WS::STAGE_BYTES, &p.s->full[slot]);
     }
   } else if (p.role == 2) {
     const uint32_t ready_parity = p.n_ready & 1;

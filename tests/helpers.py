@@ -44,16 +44,17 @@ def per_molecule_rel_err(a, b, batch_node):
     return torch.tensor(out)
 
 
-def assert_gradient_parity(got, ref32, ref64, batch_node, what=""):
+def assert_gradient_parity(got, ref32, ref64, batch_node, what="", median_bar=5e-5):
     """Parity bar for d objective / d pos (guidance).  The function is piecewise smooth (80+ ReLU layers), so a
     pre-activation within ~1e-7 of zero flips its mask between ANY two fp32 evaluation orders and moves that one
     molecule's gradient by 1e-3..1e-2 -- the reference's own fp32 autograd does this against its fp64 self
     (measured: 4 of 24 molecules beyond 1e-4, max 2e-2; DESIGN.md "guidance gradient parity").  Hence:
-      * the typical (median) molecule must match to 5e-5 (2x tighter than the 1e-4 bar; measured 2e-6 .. 2e-5),
+      * the typical (median) molecule must match to `median_bar` = 5e-5 (2x tighter than the 1e-4 bar; measured
+        2e-6 .. 2e-5 for the guidance objectives; callers with a harder upstream gradient pass the 1e-4 bar itself),
       * a majority of molecules must individually meet 1e-4, none may be off by more than 5e-2,
       * against the fp64 truth we may not be worse than the fp32 reference itself is (small-sample slack)."""
     e32 = per_molecule_rel_err(got, ref32, batch_node)
-    assert float(e32.median()) < 5e-5, (what, "median", float(e32.median()))
+    assert float(e32.median()) < median_bar, (what, "median", float(e32.median()))
     assert float((e32 < 1e-4).float().mean()) >= 0.5, (what, e32)
     assert float(e32.max()) < 5e-2, (what, float(e32.max()))
     if ref64 is not None:
