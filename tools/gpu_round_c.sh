@@ -10,7 +10,7 @@ timeout 600 python bench.py > $O/bench_guided.json 2> $O/bench_guided.err
 timeout 300 python bench.py --workload unguided --no-cpu-baseline > $O/bench_unguided.json 2> $O/bench_unguided.err
 timeout 300 python tools/tc_phase_times.py > $O/phase_times_fwd16.txt 2>&1
 timeout 300 python tools/tc_phase_times_bwd.py > $O/phase_times_bwd16.txt 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches.csv \
    python bench.py --workload guided --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_launch.log 2>&1
 for k in tc_nodeblock_fwd16 tc_nodeblock_bwd16 tc_bondffn_fwd tc_bondffn_bwd tc_edge_d tc_node_kernel bwd_node_kernel bwd_edge_tail transition_step; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 1 -c 1 -f -o $O/full_$k \
