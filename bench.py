@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "guided", "unguided"])
     ap.add_argument("--batch", type=int, default=256, help="molecules per GPU (BASELINE config 2: 256)")
+    ap.add_argument("--max-size", type=int, default=None,
+                    help="every molecule has exactly this many atoms (reference make_data_placeholder(max_size=...); "
+                         "BASELINE config 5: --batch 8192 --max-size 29 --workload unguided)")
     ap.add_argument("--cpu-batch", type=int, default=None, help="molecules in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -208,7 +211,7 @@ def main():
 
     B = args.batch
     np.random.seed(2023 + rank)
-    ph = make_data_placeholder(B)
+    ph = make_data_placeholder(B, max_size=args.max_size)
     host = {k: v.pin_memory() for k, v in ph.items()}
     d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     N, Eh = len(ph["batch_node"]), len(ph["batch_halfedge"])
@@ -320,7 +323,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"sample_MolDiff.yml {workload}: one loop body of the 1000-step sampler "
                                    f"(denoiser fwd + posterior sampling" + (" + bond-predictor guidance fwd+bwd" if guidance else "")
-                                   + f"), batch_size={B}/GPU, GEOM-Drugs node-count distribution",
+                                   + f"), batch_size={B}/GPU, "
+                                   + (f"every molecule {args.max_size} atoms (QM9-sized dense batch)" if args.max_size
+                                      else "GEOM-Drugs node-count distribution"),
                        "global_batch": total_mols, "n_nodes_rank0": N, "n_edges_rank0": E, "parallelism": f"dp{world}",
                        "l2": "256 MiB flush write between timed iterations", "weights": "random-init (seed 0)"},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d},
