@@ -8,7 +8,8 @@
 // cache, needs < 100 registers, and chunk c of an epilogue is K-slice c of the next GEMM (sliced publication, tc_pipe.cuh).
 //
 // TMEM: two 256-column accumulators A0 / A1.  An epilogue that re-reads its accumulator while it publishes slices must not
-// feed a GEMM that overwrites the same accumulator:  G1 -> A1, G2 -> A0, G3 (msg) -> A1, G4 -> A0, G5 -> A0 (unsliced).
+// feed a GEMM that overwrites the same accumulator:  G1 -> A1, G2 -> A0, G3 (msg) -> A1, G4 -> A0, G5 -> A0 (its epilogue
+// keeps the 64 pre-LayerNorm values in registers instead of re-reading A0, so it can publish in slices too).
 //
 // Included by mdb_forward.cu inside its anonymous namespace (after tc_bondffn.cuh).
 #pragma once
@@ -220,32 +221,30 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
     TC_STAMP(4);
     RunStat rs = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {                // unrolled (gv[] in registers): fold the gathered row into the accumulator
-      float x[16];
+    for (int c = 0; c < 4; ++c) {                // unrolled: gv[] <- acc + gathered row stays in registers, so the
+      float x[16];                               // accumulator is drained before the first slice is published
       tc::tmem_ld16(A0 + c * 16, x);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] += gv[c * 16 + i];
-      tc::tmem_st16(A0 + c * 16, x);
+      for (int i = 0; i < 16; ++i) { x[i] += gv[c * 16 + i]; gv[c * 16 + i] = x[i]; }
       stat_add16(rs, x);
     }
-    tc::tmem_st_wait();
     const float2 ms = ln_merge_quarter(rs.mean, rs.m2, stat, row, part);
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       float x[16];
-      tc::tmem_ld16(A0 + c * 16, x);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int k = pc + c * 16 + i;
-        x[i] = fmaxf((x[i] - ms.x) * ms.y * v_g1_g[k] + v_g1_be[k], 0.f);
+        x[i] = fmaxf((gv[c * 16 + i] - ms.x) * ms.y * v_g1_g[k] + v_g1_be[k], 0.f);
       }
       store_a16(x_hi, x_lo, row, pc + c * 16, x);
+      if (MDB_NB16_SLICED) tc::rows_publish_group(p, c);
     }
-    tc::rows_publish(p);                         // unsliced: G5 overwrites the accumulator this epilogue re-reads
+    if (!MDB_NB16_SLICED) tc::rows_publish(p);
     TC_STAMP(9);
   }
   // G5: gate.net.3 -> A0                                                          graph.py:46
-  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_G2), 0, false, true, true);
+  tc::gemm<D, D, NB16_NS, NB16_PARTS>(p, x_hi, x_lo, TCW_(NB_G2), 0, false, true, true);
   if (IS_ROW) {
     tc::rows_wait_acc(p);
     TC_STAMP(5);

@@ -204,36 +204,38 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_MSG), 256, false, true, false);        // msg -> A1
   tc::gemm<C, D>(p, e_hi, e_lo, TCW_(NB_GE), 0, false, false, true);                       // a3 - gx -> A0
   if (IS_ROW) {
-    Row16 nx = ld_tab16(gxr, 0);
+    float gv[64];                                // gx[r] row part, requested before the accumulator wait
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 t4 = *reinterpret_cast<const float4*>(gxr + j * BLK_PIECE_STRIDE);
+      gv[4 * j] = t4.x; gv[4 * j + 1] = t4.y; gv[4 * j + 2] = t4.z; gv[4 * j + 3] = t4.w;
+    }
     tc::rows_wait_acc(p);
     TC_STAMP(7);
     RunStat rs = {0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {                // fold gx[r] into the accumulator; statistics
-      float x[16], g[16];
-      unpack_row16(nx, g);
-      if (c < 3) nx = ld_tab16(gxr, c + 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                // unrolled: a3 = acc + gx stays in registers (accumulator drained before
+      float x[16];                               // the first slice is published, so the next GEMM may overwrite A0)
       tc::tmem_ld16(A0 + c * 16, x);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] += g[i];
-      tc::tmem_st16(A0 + c * 16, x);
+      for (int i = 0; i < 16; ++i) { x[i] += gv[c * 16 + i]; gv[c * 16 + i] = x[i]; }
       stat_add16(rs, x);
     }
-    tc::tmem_st_wait();
     ms_g1 = ln_merge_quarter(rs.mean, rs.m2, stat, row, part);
-#pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float x[16], g[16], be[16];
-      tc::tmem_ld16(A0 + c * 16, x);
-      lds16(v_g1_g + pc + c * 16, g); lds16(v_g1_be + pc + c * 16, be);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = fmaxf((x[i] - ms_g1.x) * ms_g1.y * g[i] + be[i], 0.f);
+    for (int c = 0; c < 4; ++c) {
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = pc + c * 16 + i;
+        x[i] = fmaxf((gv[c * 16 + i] - ms_g1.x) * ms_g1.y * v_g1_g[k] + v_g1_be[k], 0.f);
+      }
       store_a16(x_hi, x_lo, row, pc + c * 16, x);
+      tc::rows_publish_group(p, c);
     }
-    tc::rows_publish(p);                         // unsliced: the next GEMM overwrites A0
     TC_STAMP(8);
   }
-  tc::gemm<D, D>(p, x_hi, x_lo, TCW_(NB_G2), 0, false, true, true);                        // gt -> A0
+  tc::gemm<D, D, NB16_NS, 4>(p, x_hi, x_lo, TCW_(NB_G2), 0, false, true, true);            // gt -> A0
   // ---- d out = dagg[l]:  d gt -> X planes ;  d msg -> scratch planes ------------------------------------------------
   if (IS_ROW) {
     const float* dout = a.dagg + (size_t)ll * D + pc;
