@@ -106,17 +106,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_f
   return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]   -- issued by ONE thread
-__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Warp-converged issue: every lane of the MMA warp executes these; ONE elected lane (elect.sync, always the same lane for
+// D[tmem] (+)= A[smem] * B[smem].  Warp-converged issue: every lane of the MMA warp executes these; ONE elected lane (elect.sync, always the same lane for
 // a full mask) issues.  Keeping the C++ control flow converged lets ptxas hold the descriptors in uniform registers
 // instead of wrapping each UTCHMMA in an R2UR + ELECT/BRA.U.ANY uniformisation loop.
 template <bool ACC_IMM, bool ACC = true>
@@ -147,22 +137,6 @@ __device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
-// same with the accumulate flag as a compile-time immediate (no setp per MMA in the issue thread's unrolled K loop)
-template <bool ACC>
-__device__ __forceinline__ void mma_f16_ss_imm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
-      : "memory");
-}
-// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed (implies before_thread_sync)
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
 // Weight images are stored multiplied by ACC_SCALE (packing.tc_image): an nn.Linear weight is O(1/sqrt(K)) ~ 0.03, whose
 // fp16 remainder plane would sit in the subnormal range (20 significant bits); x256 puts |w| >= 5e-4 at the full 22.
 // TMEM accumulators therefore hold ACC_SCALE x the logical value: every TMEM read multiplies by 1 / ACC_SCALE (exact,

@@ -325,78 +325,6 @@ __device__ __forceinline__ float2 exchange_half(float2* stat, int row, int half,
   return o;
 }
 
-// d (in: gradient w.r.t. relu(LN(a) * g + b) for this thread's 128 columns; out: gradient w.r.t. a), where the
-// pre-LayerNorm activations a = acc (TMEM, columns taddr..+128) + bias (optional) + extra row (optional) are
-// re-read from the accumulator chunk by chunk instead of being stored.
-template <bool HAS_BIAS, bool HAS_EXTRA>
-__device__ __forceinline__ void ln_bwd_half(uint32_t taddr, const float* __restrict__ bias, const float* __restrict__ extra,
-                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            float (&d)[128], float2* stat, int row, int half) {
-  auto pre = [&](int c0, float (&a)[32]) {       // a <- pre-LN activations of columns [c0, c0 + 32)
-    tc::tmem_ld32(taddr + c0, a);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (HAS_BIAS) { a[i] += bias[c0 + i]; a[i + 1] += bias[c0 + i + 1]; a[i + 2] += bias[c0 + i + 2]; a[i + 3] += bias[c0 + i + 3]; }
-      if (HAS_EXTRA) {
-        const float4 x = *reinterpret_cast<const float4*>(extra + c0 + i);
-        a[i] += x.x; a[i + 1] += x.y; a[i + 2] += x.z; a[i + 3] += x.w;
-      }
-    }
-  };
-  float s = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
-    float a[32];
-    pre(c0, a);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += a[i];
-  }
-  const float m_h = s * (1.f / 128.f);
-  float q = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
-    float a[32];
-    pre(c0, a);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { const float t = a[i] - m_h; q = fmaf(t, t, q); }
-  }
-  const float2 o = exchange_half(stat, row, half, m_h, q);
-  const float mean = 0.5f * (m_h + o.x);
-  const float dm = m_h - o.x;
-  const float rstd = 1.f / sqrtf((q + o.y + dm * dm * 64.f) * (1.f / 256.f) + LN_EPS);
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    float a[32];
-    pre(cc * 32, a);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      const float gg[4] = {gamma[cc * 32 + i], gamma[cc * 32 + i + 1], gamma[cc * 32 + i + 2], gamma[cc * 32 + i + 3]};
-      const float bb[4] = {beta[cc * 32 + i], beta[cc * 32 + i + 1], beta[cc * 32 + i + 2], beta[cc * 32 + i + 3]};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float xh = (a[i + u] - mean) * rstd;
-        const float dxh = (xh * gg[u] + bb[u] > 0.f) ? d[cc * 32 + i + u] * gg[u] : 0.f;
-        d[cc * 32 + i + u] = dxh;
-        s1 += dxh;
-        s2 = fmaf(dxh, xh, s2);
-      }
-    }
-  }
-  const float2 o2 = exchange_half(stat, row, half, s1, s2);
-  const float m1 = (s1 + o2.x) * (1.f / 256.f), m2 = (s2 + o2.y) * (1.f / 256.f);
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    float a[32];
-    pre(cc * 32, a);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float xh = (a[i] - mean) * rstd;
-      d[cc * 32 + i] = rstd * (d[cc * 32 + i] - m1 - xh * m2);
-    }
-  }
-}
-
 // v[i] = f(i, acc[i], v[i]) over this thread's 128 accumulator columns, read in four 32-column chunks with the next chunk's
 // TMEM load in flight; v[] holds an operand gathered BEFORE the accumulator wait (peak registers 128 + 2 x 32).
 template <typename F>

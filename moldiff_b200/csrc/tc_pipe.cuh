@@ -1,10 +1,13 @@
 // Warp-specialised GEMM pipeline on top of tc_engine.cuh, shared by every tensor-core kernel of the path.
 //
-// CTA = NRW row warps + 2: the row warps (4 or 8) build the A operand and run every epilogue from TMEM (thread t
-// of warp w owns tile row 32 * (w % 4) + t = its TMEM lane; with 8 row warps, warps 4-7 take the upper half of
-// the columns of the same rows), lane 0 of the next warp streams weight stages L2 -> smem with cp.async.bulk,
-// lane 0 of the last warp issues tcgen05.mma.  All three roles walk the same static sequence of GEMMs; they meet only on
-// mbarriers:
+// CTA = NRW row warps + 2 (+ 2 idle warps in the role-split kernels, whose warpgroups trade registers with setmaxnreg):
+// the row warps (8 or 16) build the A operand and run every epilogue from TMEM (thread t of warp w owns tile row
+// 32 * (w % 4) + t = its TMEM lane; warps 4.. take further column slices of the same rows); the next warp streams weight
+// stages L2 -> smem with cp.async.bulk; the last warp issues tcgen05.mma.  The producer and MMA warps run CONVERGED: all 32
+// lanes walk the loop and wait on the mbarriers, one elect.sync-predicated lane issues (a single diverged lane made ptxas
+// wrap every UBLKCP / UTCHMMA / UTCBAR in an R2UR + ELECT / BRA.U.ANY uniformisation loop, ~60 serial instructions per K
+// step -- the pace-maker of every GEMM phase before this change).  All three roles walk the same static sequence of GEMMs;
+// they meet only on mbarriers:
 //     a_ready[g] (one arrival per row warp)  rows -> MMA   "A planes (K-slice g) written, previous accumulator drained"
 //     full[s] / empty[s]      producer <-> MMA, one weight stage each (empty is signalled by tcgen05.commit)
 //     done                    MMA -> rows   "accumulator complete"
