@@ -247,3 +247,22 @@ def test_sharding_and_gather_gloo_world2():
     other = [r for r in res if len(r) == 3][0]
     assert root[0] == 7 and root[3] == 6                     # 7 molecules, ids renumbered 0..6
     assert root[1] > other[0] and root[2] > other[1]         # rank 0's + rank 1's atoms / half-edges
+
+
+def test_new_ops_refuse_cpu_tensors():
+    """No CPU / eager fallback behind the round-1 additions either: the fused transition step, the batch decode and the edge
+    builders raise on CPU tensors instead of computing something (the unfused PyTorch transition operators remain the
+    definition that `MolDiff.sample_step` uses for CPU tensors -- host logic, not a fallback of a CUDA op)."""
+    import pytest
+    from moldiff_b200 import engine
+    from moldiff_b200.decode import decode_batch
+    from moldiff_b200.graph_build import knn_graph, radius_graph
+    pos = torch.randn(5, 3)
+    with pytest.raises(engine.MoldiffB200Error):
+        radius_graph(pos, 2.0)
+    with pytest.raises(engine.MoldiffB200Error):
+        knn_graph(pos, 2)
+    b = torch.zeros(5, dtype=torch.long)
+    he = torch.triu_indices(5, 5, 1)
+    with pytest.raises(engine.MoldiffB200Error):
+        decode_batch(torch.randn(5, 8), pos, torch.randn(10, 6), 1, b, he, torch.zeros(10, dtype=torch.long))
