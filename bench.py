@@ -293,7 +293,7 @@ def main():
                 "traffic_source": "profiles/r01_ncu_metrics.json (ncu --set full, one launch)" if traffic.get(name) else None,
                 "per_kernel_tflops_as_written": per_kernel_tf,
                 "avg_launch_ms": avg_ms, "note": "achieved = reference-as-written GEMM FLOPs of the layer part this kernel computes / CUDA-event time; "
-                        "tc_* kernels execute them as 3 split-bf16 tcgen05 MMAs after per-node hoisting, others as fp32 FFMA",
+                        "tc_* kernels execute them as 3 split-fp16 (hi|lo) tcgen05 MMAs after per-node hoisting, others as fp32 FFMA",
                 "hbm_algorithmic_gbs": (512.0 * E + 2080.0 * N) / (avg_ms * 1e-3) / 1e9,
                 "share_of_step": info["ms_total"] / max(sum(v["ms_total"] for v in prof.values()), 1e-9),
                 "per_kernel_ms": {k: round(v["ms_total"] / 3, 4) for k, v in prof.items()}}
