@@ -102,7 +102,7 @@ enum mdb_head_slot {
   MDB_NUM_HEAD_SLOTS
 };
 
-/* Tensor-core operand images of one block (byte offsets into the tc blob): per-K-stage split-bf16 (hi | lo)
+/* Tensor-core operand images of one block (byte offsets into the tc blob): per-K-stage split-fp16 (hi | lo)
  * planes of the "N x K, K-major" B operand in the UMMA SWIZZLE_NONE canonical layout (csrc/tc_engine.cuh). */
 #define MDB_TC_SLOTS(X)                                                                            \
   X(NB_EN1) X(NB_EN2) X(NB_MSG) X(NB_GE) X(NB_G2)          /* NodeBlock per-edge Linears, forward   */ \
@@ -271,7 +271,7 @@ const char* mdb_kernel_class_name(int cls);
 int mdb_num_kernel_classes(void);
 
 /* Self-test of the tcgen05 GEMM pipeline (one 128-row tile): y[128][n] = x[128][k] * W, W given as the packed
- * split-bf16 stage images of moldiff_b200/packing.py:tc_image; twice != 0 accumulates the product twice. */
+ * split-fp16 stage images of moldiff_b200/packing.py:tc_image; twice != 0 accumulates the product twice. */
 int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int32_t n, int32_t twice, void* stream);
 
 /* Debug: device int64 buffer [n_tiles][32] that tc_nodeblock_fwd_kernel fills with clock64() phase stamps of its row

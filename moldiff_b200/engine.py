@@ -127,7 +127,7 @@ KERNEL_LOGICAL_FLOP_PER_EDGE = {
                      + 2 * (256 * 64 + 64 * 64) + 64 * 256 + 64 * 256 + 256 * 256 + 256 + 129 * 32 + 32),
     # input-gradient backward of the NodeBlock per-edge Linears as autograd executes them (one dX = dY W per Linear)
     "bwd_edge_nodeblock": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
-    # tensor-core kernels: same reference Linears (as written), executed as 3 split-bf16 MMAs per product after hoisting
+    # tensor-core kernels: same reference Linears (as written), executed as 3 split-fp16 MMAs per product after hoisting
     "tc_nodeblock": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
     "tc_nodeblock_bwd": 2.0 * (64 * 256 + 256 * 256 + 256 * 256 + 321 * 256 + 256 * 256),
     "tc_bondffn": 2.0 * (80 * 64 + 2 * (64 * 128 + 256 * 128 + 128 * 128 + 128 * 64 + 321 * 32 + 32 * 64)),
@@ -208,7 +208,7 @@ class PackedNet:
         for b in range(MAX_BLOCKS):
             for s in range(NUM_BLOCK):
                 d.block_off[b][s] = block_off[b][s] if b < num_blocks else -1
-        # tensor-core operand images (tcgen05 split-bf16 path); MDB_DISABLE_TC=1 keeps the fp32 FFMA kernels
+        # tensor-core operand images (tcgen05 split-fp16 path); MDB_DISABLE_TC=1 keeps the fp32 FFMA kernels
         self.tc_blob = None
         d.tc_blob = None
         for b in range(MAX_BLOCKS):
@@ -399,7 +399,7 @@ def bondpred_backward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, 
 
 
 def tc_selftest(x, w_kn, twice=False):
-    """y = x @ w (x [128][K], w [K][N]) through the tcgen05 split-bf16 pipeline (tests only)."""
+    """y = x @ w (x [128][K], w [K][N]) through the tcgen05 split-fp16 pipeline (tests only)."""
     lib = load_library()
     x = _dev_f32(x, "x")
     k, n = w_kn.shape
