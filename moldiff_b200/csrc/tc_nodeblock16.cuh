@@ -126,24 +126,29 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
 
   // Persistent CTA: TMEM, barriers and the parameter vectors are set up once; the pipeline counters and mbarrier phases
   // simply keep running across tiles, and the producer prefetches the next tile's first weight stages during the tail.
-#pragma unroll 1
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-  const int q0 = tile * tc::ROWS;
-  TC_STAMP(0);
-  if (a.dbg) p.dbg = a.dbg + (size_t)tile * 32;
-  int my_r = -1;
-  float e16[16];                              // this thread's 16 columns of the e tile
-  if (IS_ROW) {
-    const int q = q0 + row;
+  // this thread's inputs of a tile: 16 columns of e and the row's endpoints.  Loaded one tile AHEAD (during the previous
+  // tile's last epilogue), so the tile starts without an exposed L2 round trip.
+  float e16[16];
+  int nxt_r = -1, nxt_l = -1;
+  auto load_tile_inputs = [&](int t) {
+    const int q = t * tc::ROWS + row;
+    const bool in = t < n_tiles && q < a.n_edges;
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q < a.n_edges) x = *reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C + part * 16 + i);
+      if (in) x = *reinterpret_cast<const float4*>(a.ebuf + (size_t)q * C + part * 16 + i);
       e16[i] = x.x; e16[i + 1] = x.y; e16[i + 2] = x.z; e16[i + 3] = x.w;
     }
-    if (q < a.n_edges) { my_r = a.right[q]; if (part == 0) ls[row] = a.left[q]; }
-    else if (part == 0) ls[row] = -1;
-  }
+    nxt_r = in ? a.right[q] : -1;
+    nxt_l = in ? a.left[q] : -1;
+  };
+  if (IS_ROW) load_tile_inputs(blockIdx.x);
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  TC_STAMP(0);
+  if (a.dbg) p.dbg = a.dbg + (size_t)tile * 32;
+  const int my_r = nxt_r;
+  if (IS_ROW && part == 0) ls[row] = nxt_l;
   const int rr = my_r < 0 ? 0 : my_r;
   TC_STAMP(1);
 
@@ -248,6 +253,7 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   if (IS_ROW) {
     tc::rows_wait_acc(p);
     TC_STAMP(5);
+    load_tile_inputs(tile + gridDim.x);          // next tile's inputs: in flight under this epilogue and the reduction
     // out = (msg + b) * sigmoid(gate + b)  -> smem tile (all operand planes are dead now)     graph.py:47
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
