@@ -164,7 +164,7 @@ def run_reference(args, workload):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    B = args.cpu_batch or (8 if workload == "guided" else 16)
+    B = args.cpu_batch or (32 if workload == "guided" else 64)
     times = []
     _ = cpu_step_seconds(workload, B, threads, reps=0) if args.warmup > 0 else None
     steps = max(1, min(args.steps, 5))
@@ -312,7 +312,7 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            cb = args.cpu_batch or (8 if workload == "guided" else 16)
+            cb = args.cpu_batch or (32 if workload == "guided" else 64)
             sec, cn, ceh = cpu_step_seconds(workload, cb, threads, reps=2)
             cpu = {"value": cb / (T_STEPS * sec), "unit": "molecules/s", "cores": threads, "kind": "port",
                    "sample": f"min of 2 loop bodies at B={cb} (N={cn}, E={2 * ceh}) after 1 warm-up; "
