@@ -271,7 +271,8 @@ const char* mdb_kernel_class_name(int cls);
 int mdb_num_kernel_classes(void);
 
 /* Self-test of the tcgen05 GEMM pipeline (one 128-row tile): y[128][n] = x[128][k] * W, W given as the packed
- * split-fp16 stage images of moldiff_b200/packing.py:tc_image; twice != 0 accumulates the product twice. */
+ * split-fp16 stage images of moldiff_b200/packing.py:tc_image; `twice` bit 0 accumulates the product twice, bit 1 selects
+ * the cross-first accumulation order (csrc/tc_pipe.cuh) that the bond predictor's forward kernels use. */
 int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int32_t n, int32_t twice, void* stream);
 
 /* Debug: device int64 buffer [n_tiles][32] that tc_nodeblock_fwd_kernel fills with clock64() phase stamps of its row

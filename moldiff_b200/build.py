@@ -24,18 +24,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant / defines: an A/B library libmoldiff_b200_<variant>.so compiled with extra -D flags (selected at run time
+    with MDB_LIB_VARIANT=<variant>); the default call builds the product library."""
+    lib = LIB if not variant else LIB[:-3] + "_" + variant + ".so"
+    if not variant and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("MDB_NVCC_EXTRA", "").split()      # e.g. -DMDB_NB16_SLICED=0 for A/B experiments
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    extra = os.environ.get("MDB_NVCC_EXTRA", "").split() + ["-D" + d for d in defines]
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -764,7 +764,7 @@ struct Saved {
   float *ddect;              // [N][64]
   float *gamax;              // [32]: word 0 = bit pattern of max |d_logits| of the current backward call
   float *hnb, *gxb;          // [L][pad64(N)][256]  node-blocked copies of the saved hn / gx tables
-  float *scr_he, *scr_dm;    // [ceil(E/128)*128][256] each: tc_nodeblock_bwd16 scratch slabs (he fp32 / d msg operand planes)
+  float *scr_he, *scr_dm;    // [persistent CTAs * 128][256] each: tc_nodeblock_bwd16 scratch slabs (he fp32 / d msg operand planes)
 };
 
 constexpr int TAB_FLOATS = 3 * D + 2 * 128 + 2 * 32 + 2 * C;   // per node
@@ -792,8 +792,8 @@ size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   sv.hnb = take(L * pad64(N) * D); sv.gxb = take(L * pad64(N) * D);
   sv.dnl = take(2 * N * 128); sv.dgn = take(2 * N * 32); sv.ddect = take(N * C);
   sv.gamax = take(32);
-  const int64_t e_pad = (E + 127) / 128 * 128;
-  sv.scr_he = take(e_pad * D); sv.scr_dm = take(e_pad * D);
+  const int64_t scr_rows = (int64_t)persistent_grid((E + 127) / 128) * 128;   // one 128-row slab per persistent CTA
+  sv.scr_he = take(scr_rows * D); sv.scr_dm = take(scr_rows * D);
   return o;
 }
 
@@ -815,10 +815,14 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(edge_kernel_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_EDGE_D));
   CUDA_TRY(cudaFuncSetAttribute(edge_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DEC));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB));
-  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
-  CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
-  CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
-  CUDA_TRY(cudaFuncSetAttribute(tc_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NODE));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
+  CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
+  CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
+  CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
+  CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
+  CUDA_TRY(cudaFuncSetAttribute(tc_node_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NODE));
+  CUDA_TRY(cudaFuncSetAttribute(tc_node_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NODE));
   done = true;
   return MDB_OK;
 }
@@ -834,6 +838,14 @@ struct FwdIn {
   float *out_node, *out_pos, *out_edge;        // kind 0: h_node/pos/h_edge; kind 1: preds; kind 2: logits in out_edge
   int save;                                    // keep per-block inputs for the backward pass
 };
+
+// Accumulation order of a network's forward GEMMs (tc_pipe.cuh: gemm): cross-first for the bond predictor, whose forward
+// activations feed the guidance gradient (the hardware's truncating accumulate costs 1.4e-4 there in the interleaved order,
+// 1e-5 in this one); MDB_CROSS_FIRST=0 / 1 forces it off / on for every network (A/B runs).
+bool cross_first(const mdb_net_desc* net) {
+  static const int env = []() { const char* e = getenv("MDB_CROSS_FIRST"); return e == nullptr ? -1 : (e[0] != '0' ? 1 : 0); }();
+  return env >= 0 ? env == 1 : net->kind == 2;
+}
 
 // node kernel launch: tensor-core version when its operand images are packed, FFMA version otherwise
 int launch_node(const mdb_net_desc* net, const NodeArgs& na, int blk_mid, int blk_pre, int node_tiles, cudaStream_t st) {
@@ -860,8 +872,9 @@ int launch_node(const mdb_net_desc* net, const NodeArgs& na, int blk_mid, int bl
   ta.pos_cur = na.pos_cur; ta.pos_nxt = na.pos_nxt; ta.pred_node = na.pred_node;
   fill_node_vecs(ta.v, net->blob_host, na.do_mid ? &na.mid : nullptr, na.do_pre ? &na.pre : nullptr,
                  na.do_dec ? &na.head : nullptr, na.kind, na.update_pos != 0);
-  LAUNCH(MDB_K_tc_node, st,
-         (tc_node_kernel<<<(na.n_nodes + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NODE, st>>>(ta)));
+  const int grid = (na.n_nodes + tc::ROWS - 1) / tc::ROWS;
+  if (cross_first(net)) LAUNCH(MDB_K_tc_node, st, (tc_node_kernel<true><<<grid, TC_NB_THREADS, SMEM_TC_NODE, st>>>(ta)));
+  else LAUNCH(MDB_K_tc_node, st, (tc_node_kernel<false><<<grid, TC_NB_THREADS, SMEM_TC_NODE, st>>>(ta)));
   return MDB_OK;
 }
 
@@ -896,6 +909,7 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   HeadOff head;
   for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
   const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
+  const bool xf = cross_first(net);
 
   LAUNCH(MDB_K_node_init, st,
          (node_init_kernel<<<N, D, 0, st>>>(net->kind, N, net->num_node_types, net->time_dim, net->num_timesteps,
@@ -948,8 +962,10 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       fa.pos = pos_cur; fa.rbf_lo = net->rbf_start; fa.rbf_hi = net->rbf_stop; fa.ebuf = ea.ebuf; fa.sl = ea.sl;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
       fa.dbg = g_dbg_sel == 2 ? g_dbg_stamps : nullptr;
-      LAUNCH(MDB_K_tc_bondffn, st,
-             (tc_bondffn_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
+      if (xf) LAUNCH(MDB_K_tc_bondffn, st,
+                     (tc_bondffn_fwd_kernel<true><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
+      else LAUNCH(MDB_K_tc_bondffn, st,
+                  (tc_bondffn_fwd_kernel<false><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
     } else if (E > 0) {
       LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
     }
@@ -963,8 +979,9 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       fill_nb_vecs(ta.v, net->blob_host, ea.off);
       static const bool nb16 = []() { const char* e = getenv("MDB_TC_NB16"); return e == nullptr || e[0] != '0'; }();
       if (nb16) {
-        LAUNCH(MDB_K_tc_nodeblock, st,
-               (tc_nodeblock_fwd16_kernel<<<persistent_grid((E + tc::ROWS - 1) / tc::ROWS), NB16_THREADS, SMEM_TC_NB16, st>>>(ta)));
+        const int grid = persistent_grid((E + tc::ROWS - 1) / tc::ROWS);
+        if (xf) LAUNCH(MDB_K_tc_nodeblock, st, (tc_nodeblock_fwd16_kernel<true><<<grid, NB16_THREADS, SMEM_TC_NB16, st>>>(ta)));
+        else LAUNCH(MDB_K_tc_nodeblock, st, (tc_nodeblock_fwd16_kernel<false><<<grid, NB16_THREADS, SMEM_TC_NB16, st>>>(ta)));
       } else {
         LAUNCH(MDB_K_tc_nodeblock, st,
                (tc_nodeblock_fwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_NB, st>>>(ta)));
@@ -988,8 +1005,10 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       da.left = plan->left; da.right = plan->right; da.n_nodes = N; da.n_edges = E; da.update_pos = net->update_pos;
       da.ebuf = ea.ebuf; da.sl = ea.sl; da.fl = ea.fl; da.fr = ea.fr; da.pos_cur = pos_cur; da.pos_nxt = pos_nxt;
       fill_edge_d_vecs(da.v, net->blob_host, ea.off, net->update_pos != 0);
-      LAUNCH(MDB_K_tc_edge_d, st,
-             (tc_edge_d_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, st>>>(da)));
+      if (xf) LAUNCH(MDB_K_tc_edge_d, st,
+                     (tc_edge_d_kernel<true><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, st>>>(da)));
+      else LAUNCH(MDB_K_tc_edge_d, st,
+                  (tc_edge_d_kernel<false><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, st>>>(da)));
     } else if (E > 0) {
       LAUNCH(MDB_K_edge_d, st, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea)));
     }
@@ -1141,6 +1160,16 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
 
 int mdb_tc_selftest(const float* x, const void* w_img, float* y, int32_t k, int32_t n, int32_t twice, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (twice & 2) {   // bit 1: cross-first accumulation order
+    twice &= 1;
+    if (k == 64 && n == 256) return launch_tc_selftest<64, 256, true>(x, w_img, y, twice, st);
+    if (k == 256 && n == 256) return launch_tc_selftest<256, 256, true>(x, w_img, y, twice, st);
+    if (k == 256 && n == 64) return launch_tc_selftest<256, 64, true>(x, w_img, y, twice, st);
+    if (k == 128 && n == 128) return launch_tc_selftest<128, 128, true>(x, w_img, y, twice, st);
+    if (k == 80 && n == 64) return launch_tc_selftest<80, 64, true>(x, w_img, y, twice, st);
+    if (k == 64 && n == 32) return launch_tc_selftest<64, 32, true>(x, w_img, y, twice, st);
+    return fail(MDB_EINVAL, "mdb_tc_selftest: unsupported (k, n) for the cross-first order%s");
+  }
   if (k == 64 && n == 256) return launch_tc_selftest<64, 256>(x, w_img, y, twice, st);
   if (k == 256 && n == 256) return launch_tc_selftest<256, 256>(x, w_img, y, twice, st);
   if (k == 256 && n == 64) return launch_tc_selftest<256, 64>(x, w_img, y, twice, st);

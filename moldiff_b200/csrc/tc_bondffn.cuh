@@ -80,6 +80,7 @@ __device__ __forceinline__ void gather_n(const float* __restrict__ src, float (&
 
 constexpr int FFN_O_LD = 68;    // fp32 row stride of the o tile: 272 B = 16 (mod 128)
 
+template <bool XF>   // cross-first accumulation order (tc_pipe.cuh)
 __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const __grid_constant__ TcFfnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int KI = C + G;                                  // 80
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bondffn_fwd_kernel(const 
   FFN_STAMP(0);
   const int q0 = blockIdx.x * tc::ROWS;
   const Tables& tb = a.tb;
-  tc::Pipe p;
+  tc::PipeT<tc::NSTAGE, XF> p;
   tc::pipe_init<TC_NRW>(p, ps, stages);
   if (warp == TC_NRW) tc::tmem_alloc<256>(&ps->tmem_base);
   const int row = (warp & 3) * 32 + lane;

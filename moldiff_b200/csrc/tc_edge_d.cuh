@@ -27,6 +27,7 @@ struct TcEdgeDArgs {
   EdgeDVecs v;
 };
 
+template <bool XF>   // cross-first accumulation order (tc_pipe.cuh)
 __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_edge_d_kernel(const __grid_constant__ TcEdgeDArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* h_hi = smem_raw;                                  // region A: e planes, then new-h_edge planes (K = 64)
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_edge_d_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * tc::ROWS;
   const Tables& tb = a.tb;
-  tc::Pipe p;
+  tc::PipeT<tc::NSTAGE, XF> p;
   tc::pipe_init<TC_NRW>(p, ps, stages);
   if (warp == TC_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
   const int row = (warp & 3) * 32 + lane;

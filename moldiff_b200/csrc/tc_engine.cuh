@@ -71,6 +71,24 @@ __device__ __forceinline__ void stage_load_elect(void* dst_smem, const void* src
       : "memory");
 }
 
+// Two bulk copies (n2 = 0: one) landing on one barrier phase: the second pass of a cross-first GEMM (tc_pipe.cuh) brings the hi
+// planes of two K steps into one ring slot.
+__device__ __forceinline__ void stage_load2_elect(void* dst_smem, const void* src0, const void* src1, uint32_t bytes_each,
+                                                  uint32_t n2, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e, q;\n\t.reg .b32 tot, d1;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "and.pred q, q, e;\n\t"
+      "mad.lo.u32 tot, %5, %3, %3;\n\t"
+      "add.u32 d1, %0, %3;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%4], tot;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %3, [%4];\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%2], %3, [%4];\n\t}" ::"r"(smem_u32(dst_smem)),
+      "l"(src0), "l"(src1), "r"(bytes_each), "r"(smem_u32(bar)), "r"(n2)
+      : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // generic-proxy GLOBAL writes -> visible to the async proxy (a later cp.async.bulk that reads them back)
@@ -305,6 +323,9 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 
 // sigmoid for the tensor-core path: ex2.approx + rcp.approx (~1e-6 relative), 2 MUFU + 3 FP ops
 __device__ __forceinline__ float fast_sigmoid(float x) {
+#ifdef MDB_EXACT_SIGMOID              // A/B build for the numerics study (tools/tc_numerics.py)
+  return 1.f / (1.f + expf(-x));
+#endif
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));

@@ -57,6 +57,7 @@ __device__ __forceinline__ void store_rowN(float* __restrict__ dst, const float 
   for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
 
+template <bool XF>   // cross-first accumulation order (tc_pipe.cuh)
 __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_node_kernel(const __grid_constant__ TcNodeArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* p_hi = smem_raw;                                  // K = 256 planes (h_node / hidden activations)
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_node_kernel(const __grid_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * tc::ROWS;
   const Tables& tb = a.tb;
-  tc::Pipe p;
+  tc::PipeT<tc::NSTAGE, XF> p;
   tc::pipe_init<TC_NRW>(p, ps, stages);
   if (warp == TC_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
   const int row = (warp & 3) * 32 + lane;

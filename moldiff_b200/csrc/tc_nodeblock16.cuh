@@ -77,7 +77,7 @@ __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int r, i
   }
 }
 
-template <bool IS_ROW>
+template <bool IS_ROW, bool XF>
 __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* e_hi = smem_raw;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Tables& tb = a.tb;
   const int n_tiles = (a.n_edges + tc::ROWS - 1) / tc::ROWS;
-  Pipe16 p;
+  tc::PipeT<NB16_NS, XF> p;
   tc::pipe_init_split<NB16_NRW, IS_ROW, NB16_NS>(p, ps, stages);
   if (warp == NB16_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
   const int row = (warp & 3) * 32 + lane;
@@ -302,13 +302,15 @@ __device__ __forceinline__ void tc_nodeblock_fwd16_body(const TcNbArgs& a) {
 }
 
 // 640 threads compile to 96 registers; the producer/MMA warpgroup keeps 32, the four row warpgroups get 112 (inc and dec must balance inside the CTA pool: 512 x 16 = 128 x 64 -- an unbalanced inc blocks forever).
+// XF: cross-first accumulation order (tc_pipe.cuh) -- the bond predictor's forward, whose activations feed the guidance gradient
+template <bool XF>
 __global__ void __launch_bounds__(NB16_THREADS, 1) tc_nodeblock_fwd16_kernel(const __grid_constant__ TcNbArgs a) {
   if (threadIdx.x < NB16_NRW * 32) {
     tc::reg_alloc<112>();
-    tc_nodeblock_fwd16_body<true>(a);
+    tc_nodeblock_fwd16_body<true, XF>(a);
   } else {
     tc::reg_dealloc<32>();
-    tc_nodeblock_fwd16_body<false>(a);
+    tc_nodeblock_fwd16_body<false, XF>(a);
   }
 }
 

@@ -38,8 +38,8 @@ struct TcNbBwd16Args {
   const float* dagg;     // [N][256] d/d (aggregated messages)
   float *dgx, *dhn;      // [pad64(N)][256] scatter targets (pre-zeroed), NODE-BLOCKED layout (tile_engine.cuh: blk_off)
   float* de;             // [E][64]  d/d e, accumulated (+=)
-  float* scr_he;         // [tiles * 128][256] fp32 scratch
-  uint8_t* scr_dm;       // [tiles][2][64 KB] d msg as A-operand planes
+  float* scr_he;         // [gridDim.x * 128][256] fp32 scratch, one slab per (persistent) CTA
+  uint8_t* scr_dm;       // [gridDim.x][2][64 KB] d msg as A-operand planes
   long long* dbg;
 };
 
@@ -139,8 +139,11 @@ __device__ __forceinline__ void tc_nodeblock_bwd16_body(const TcNbBwd16Args& a) 
   const float* gxr = tb.gxb + blk_off(rr, pc / 4);
   // he scratch, tile-blocked so that a warp instruction (32 consecutive rows, one 16-byte piece each) touches 4 lines
   // instead of 32: [tile][16-byte column piece 0..63][row 0..127][4 floats]
-  float* he_scr = a.scr_he + (size_t)tile * tc::ROWS * D + (size_t)(pc / 4) * tc::ROWS * 4 + row * 4;
-  uint8_t* dm_scr = a.scr_dm + (size_t)tile * 2 * PLANE256_BYTES;
+  // Both slabs are indexed by CTA, not by tile: the kernel is persistent, a CTA finishes with its slab (same threads write
+  // and read he; the d msg planes are read back by the bulk copy long before the next tile's epilogue rewrites them)
+  // before its next tile, so gridDim.x x 256 KB (38 MB) stays L2-resident instead of tiles x 256 KB of write-backs.
+  float* he_scr = a.scr_he + (size_t)blockIdx.x * tc::ROWS * D + (size_t)(pc / 4) * tc::ROWS * 4 + row * 4;
+  uint8_t* dm_scr = a.scr_dm + (size_t)blockIdx.x * 2 * PLANE256_BYTES;
   float2 ms_en1 = make_float2(0.f, 1.f), ms_g1 = make_float2(0.f, 1.f);
   float de16[16];
 

@@ -4,7 +4,7 @@
 #pragma once
 #include "tc_pipe.cuh"
 
-template <int K, int N>
+template <int K, int N, bool XF = false>
 __global__ void __launch_bounds__(tc::NTHREADS_TC, 1)
 tc_selftest_kernel(const float* __restrict__ X, const uint8_t* __restrict__ w_img, float* __restrict__ Y, int twice) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -13,7 +13,7 @@ tc_selftest_kernel(const float* __restrict__ X, const uint8_t* __restrict__ w_im
   uint8_t* stages = a_lo + tc::ROWS * K * 2;
   tc::PipeSmem* ps = reinterpret_cast<tc::PipeSmem*>(stages + tc::NSTAGE * tc::STAGE_SLOT);
   const int tid = threadIdx.x, warp = tid >> 5;
-  tc::Pipe p;
+  tc::PipeT<tc::NSTAGE, XF> p;
   tc::pipe_init(p, ps, stages);
   if (warp == 4) tc::tmem_alloc<256>(&ps->tmem_base);
   tc::fence_before_sync();
@@ -45,11 +45,11 @@ tc_selftest_kernel(const float* __restrict__ X, const uint8_t* __restrict__ w_im
   if (warp == 4) { __syncwarp(); tc::tmem_dealloc<256>(ps->tmem_base); }
 }
 
-template <int K, int N>
+template <int K, int N, bool XF = false>
 int launch_tc_selftest(const float* X, const void* w_img, float* Y, int twice, cudaStream_t st) {
   const size_t smem = 2 * (size_t)tc::ROWS * K * 2 + tc::NSTAGE * tc::STAGE_SLOT + sizeof(tc::PipeSmem) + 128;
-  CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel<K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_selftest_kernel<K, N><<<1, tc::NTHREADS_TC, smem, st>>>(X, reinterpret_cast<const uint8_t*>(w_img), Y, twice);
+  CUDA_TRY(cudaFuncSetAttribute(tc_selftest_kernel<K, N, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_selftest_kernel<K, N, XF><<<1, tc::NTHREADS_TC, smem, st>>>(X, reinterpret_cast<const uint8_t*>(w_img), Y, twice);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return MDB_OK;

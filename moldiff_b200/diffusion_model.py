@@ -127,12 +127,19 @@ class MolDiff(nn.Module, _PackedMixin):
         return {"pred_node": pred_node, "pred_pos": pred_pos, "pred_halfedge": pred_half}
 
     def get_loss(self, node_type, node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge, num_mol):
-        """Forward + diffusion losses (model.py:128-201).  The fused forward does not record an autograd
-        graph: the returned losses are values (training backward is a later-round row)."""
-        device = node_pos.device
-        time_step, _ = self.sample_time(num_mol, device)
+        """Forward + diffusion losses (model.py:128-201): draw the time steps, perturb the molecule, denoise, compare."""
+        time_step, _ = self.sample_time(num_mol, node_pos.device)
         pos_pert, node_pert, half_pert = self._perturb(node_type, node_pos, batch_node, halfedge_type,
                                                        batch_halfedge, time_step)
+        return self.loss_from_perturbed(node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge, time_step,
+                                        pos_pert, node_pert, half_pert)
+
+    def loss_from_perturbed(self, node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge, time_step,
+                            pos_pert, node_pert, half_pert):
+        """The deterministic half of `get_loss` (model.py:140-201): denoise the given perturbed molecule and evaluate the
+        losses.  `node_pert` / `half_pert` are what the transitions' `add_noise` returned -- (one-hot, log q(v_t), log v_0)
+        in the discrete space, (v_t, v_0) in the continuous one.  Split out so that tests can teacher-force the reference's
+        own random draws (tests/golden/make_golden_loss.py)."""
         edge_index = torch.cat([halfedge_index, halfedge_index.flip(0)], dim=1)
         batch_edge = torch.cat([batch_halfedge, batch_halfedge], dim=0)
         discrete = self.categorical_space == "discrete"

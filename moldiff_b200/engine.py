@@ -14,7 +14,11 @@ import torch
 
 from . import packing
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmoldiff_b200.so")
+# MDB_LIB_VARIANT=<name> loads libmoldiff_b200_<name>.so, an A/B build made by moldiff_b200.build.build(variant=...)
+# (numerics / tuning studies only; the default is the one product library)
+_VARIANT = os.environ.get("MDB_LIB_VARIANT", "")
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                         f"libmoldiff_b200{'_' + _VARIANT if _VARIANT else ''}.so")
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -398,13 +402,14 @@ def bondpred_backward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, 
     return d_pos
 
 
-def tc_selftest(x, w_kn, twice=False):
+def tc_selftest(x, w_kn, twice=False, cross_first=False):
     """y = x @ w (x [128][K], w [K][N]) through the tcgen05 split-fp16 pipeline (tests only)."""
     lib = load_library()
     x = _dev_f32(x, "x")
     k, n = w_kn.shape
     img = packing.tc_image(w_kn.cpu()).to(x.device)
     y = torch.empty(128, n, dtype=torch.float32, device=x.device)
-    rc = lib.mdb_tc_selftest(x.data_ptr(), img.data_ptr(), y.data_ptr(), k, n, 1 if twice else 0, _stream_ptr(x.device))
+    rc = lib.mdb_tc_selftest(x.data_ptr(), img.data_ptr(), y.data_ptr(), k, n, (1 if twice else 0) | (2 if cross_first else 0),
+                             _stream_ptr(x.device))
     _check(rc, "mdb_tc_selftest")
     return y

@@ -176,6 +176,33 @@ def ln_relu_bwd(d, xh, rstd, g, b):
     return rstd * (dxh - m1 - xh * m2)
 
 
+_backward_mm = None
+
+
+def set_backward_mm(fn):
+    """Test hook (tools/emulate_tc_backward.py): fn(a, w, grad) replaces `a @ w` for every GEMM that the tensor-core
+    backward kernels execute (grad = True for gradient operands, False for their forward recompute)."""
+    global _backward_mm
+    _backward_mm = fn
+
+
+_forward_mm = None
+
+
+def set_forward_mm(fn):
+    """Test hook: fn(a, w) replaces `a @ w` for every GEMM of the forward half of bondpred_forward_backward."""
+    global _forward_mm
+    _forward_mm = fn
+
+
+def _fmm(a, w):
+    return a @ w if _forward_mm is None else _forward_mm(a, w)
+
+
+def _mm(a, w, grad=True):
+    return a @ w if _backward_mm is None else _backward_mm(a, w, grad)
+
+
 def bondpred_forward_backward(W: Blob, *, num_blocks, rbf_lo, rbf_hi, time_dim, T, kn, ke,
                               h_node_in, pos, edge_index, batch_node, batch_edge, t, d_logits):
     """Returns (logits, d_pos) with d_pos = d sum(logits * d_logits) / d pos, computed the way the kernels do."""
@@ -198,50 +225,50 @@ def bondpred_forward_backward(W: Blob, *, num_blocks, rbf_lo, rbf_hi, time_dim, 
 
     def tables(i, x):
         tb = {}
-        a = ln(x @ W.b(i, "NB_NN1_W", D, D) + W.b(i, "NB_NN1_B", D), W.b(i, "NB_NN1_G", D), W.b(i, "NB_NN1_BE", D))
-        tb["hn"] = a @ W.b(i, "NB_NN2_W", D, D) + W.b(i, "NB_NN2_B", D)
-        tb["gx"] = x @ W.b(i, "NB_GX_W", D, D) + W.b(i, "NB_G1_B", D) + tn[:, None] * W.b(i, "NB_GT_W", D)
-        tb["cen"] = x @ W.b(i, "NB_CEN_W", D, D) + W.b(i, "NB_CEN_B", D)
+        a = ln(_fmm(x, W.b(i, "NB_NN1_W", D, D)) + W.b(i, "NB_NN1_B", D), W.b(i, "NB_NN1_G", D), W.b(i, "NB_NN1_BE", D))
+        tb["hn"] = _fmm(a, W.b(i, "NB_NN2_W", D, D)) + W.b(i, "NB_NN2_B", D)
+        tb["gx"] = _fmm(x, W.b(i, "NB_GX_W", D, D)) + W.b(i, "NB_G1_B", D) + tn[:, None] * W.b(i, "NB_GT_W", D)
+        tb["cen"] = _fmm(x, W.b(i, "NB_CEN_W", D, D)) + W.b(i, "NB_CEN_B", D)
         for s, S in (("l", "EL"), ("r", "ER")):
-            tb["nl" + s] = x @ W.b(i, S + "_NL_W", D, 128)
-            tb["gn" + s] = x @ W.b(i, S + "_GN_W", D, 32) + W.b(i, S + "_G1_B", 32)
-        tb["fl"] = x @ W.b(i, "EB_NFL_W", D, C) + W.b(i, "EB_NFL_B", C)
-        tb["fr"] = x @ W.b(i, "EB_NFR_W", D, C) + W.b(i, "EB_NFR_B", C)
+            tb["nl" + s] = _fmm(x, W.b(i, S + "_NL_W", D, 128))
+            tb["gn" + s] = _fmm(x, W.b(i, S + "_GN_W", D, 32)) + W.b(i, S + "_G1_B", 32)
+        tb["fl"] = _fmm(x, W.b(i, "EB_NFL_W", D, C)) + W.b(i, "EB_NFL_B", C)
+        tb["fr"] = _fmm(x, W.b(i, "EB_NFR_W", D, C)) + W.b(i, "EB_NFR_B", C)
         return tb
 
     saved = []
     for i in range(num_blocks):
         tb = tables(i, x)
-        e = torch.cat([hedge, g], -1) @ W.b(i, "EE_W", C + G, C) + W.b(i, "EE_B", C)
-        a = ln(e @ W.b(i, "NB_EN1_W", C, D) + W.b(i, "NB_EN1_B", D), W.b(i, "NB_EN1_G", D), W.b(i, "NB_EN1_BE", D))
-        m = (a @ W.b(i, "NB_EN2_W", D, D) + W.b(i, "NB_EN2_B", D)) * tb["hn"][right]
-        a = ln(e @ W.b(i, "NB_GE_W", C, D) + tb["gx"][right], W.b(i, "NB_G1_G", D), W.b(i, "NB_G1_BE", D))
-        sg = torch.sigmoid(a @ W.b(i, "NB_G2_W", D, D) + W.b(i, "NB_G2_B", D))
-        agg = scatter((m @ W.b(i, "NB_MSG_W", D, D) + W.b(i, "NB_MSG_B", D)) * sg, left, N)
+        e = _fmm(torch.cat([hedge, g], -1), W.b(i, "EE_W", C + G, C)) + W.b(i, "EE_B", C)
+        a = ln(_fmm(e, W.b(i, "NB_EN1_W", C, D)) + W.b(i, "NB_EN1_B", D), W.b(i, "NB_EN1_G", D), W.b(i, "NB_EN1_BE", D))
+        m = (_fmm(a, W.b(i, "NB_EN2_W", D, D)) + W.b(i, "NB_EN2_B", D)) * tb["hn"][right]
+        a = ln(_fmm(e, W.b(i, "NB_GE_W", C, D)) + tb["gx"][right], W.b(i, "NB_G1_G", D), W.b(i, "NB_G1_BE", D))
+        sg = torch.sigmoid(_fmm(a, W.b(i, "NB_G2_W", D, D)) + W.b(i, "NB_G2_B", D))
+        agg = scatter((_fmm(m, W.b(i, "NB_MSG_W", D, D)) + W.b(i, "NB_MSG_B", D)) * sg, left, N)
         o = {}
         for s, S, node in (("l", "EL", left), ("r", "ER", right)):
-            inter = (e @ W.b(i, S + "_BL_W", C, 128)) * tb["nl" + s][node]
-            a = ln(inter @ W.b(i, S + "_I1_W", 128, 128) + W.b(i, S + "_I1_B", 128), W.b(i, S + "_I1_G", 128), W.b(i, S + "_I1_BE", 128))
-            i2 = a @ W.b(i, S + "_I2_W", 128, C) + W.b(i, S + "_I2_B", C)
-            g1 = e @ W.b(i, S + "_GB_W", C, 32) + tb["gn" + s][node] + te[:, None] * W.b(i, S + "_GT_W", 32)
+            inter = (_fmm(e, W.b(i, S + "_BL_W", C, 128))) * tb["nl" + s][node]
+            a = ln(_fmm(inter, W.b(i, S + "_I1_W", 128, 128)) + W.b(i, S + "_I1_B", 128), W.b(i, S + "_I1_G", 128), W.b(i, S + "_I1_BE", 128))
+            i2 = _fmm(a, W.b(i, S + "_I2_W", 128, C)) + W.b(i, S + "_I2_B", C)
+            g1 = _fmm(e, W.b(i, S + "_GB_W", C, 32)) + tb["gn" + s][node] + te[:, None] * W.b(i, S + "_GT_W", 32)
             g1 = ln(g1, W.b(i, S + "_G1_G", 32), W.b(i, S + "_G1_BE", 32))
-            o[s] = i2 * torch.sigmoid(g1 @ W.b(i, S + "_G2_W", 32, C) + W.b(i, S + "_G2_B", C))
+            o[s] = i2 * torch.sigmoid(_fmm(g1, W.b(i, S + "_G2_W", 32, C)) + W.b(i, S + "_G2_B", C))
         SL, SR = scatter(o["l"], right, N), scatter(o["r"], left, N)
         saved.append(dict(x=x, e=e, agg=agg, SL=SL, SR=SR))
         a = ln(tb["cen"] + agg, W.b(i, "NB_LN_G", D), W.b(i, "NB_LN_BE", D))
-        x = x + a @ W.b(i, "NB_OUT_W", D, D) + W.b(i, "NB_OUT_B", D)
-        u = e @ W.b(i, "EB_SELF_W", C, C) + W.b(i, "EB_SELF_B", C) + SL[left] + SR[right] + tb["fl"][left] + tb["fr"][right]
-        hedge = e + ln(u, W.b(i, "EB_LN_G", C), W.b(i, "EB_LN_BE", C)) @ W.b(i, "EB_OUT_W", C, C) + W.b(i, "EB_OUT_B", C)
+        x = x + _fmm(a, W.b(i, "NB_OUT_W", D, D)) + W.b(i, "NB_OUT_B", D)
+        u = _fmm(e, W.b(i, "EB_SELF_W", C, C)) + W.b(i, "EB_SELF_B", C) + SL[left] + SR[right] + tb["fl"][left] + tb["fr"][right]
+        hedge = e + _fmm(ln(u, W.b(i, "EB_LN_G", C), W.b(i, "EB_LN_BE", C)), W.b(i, "EB_OUT_W", C, C)) + W.b(i, "EB_OUT_B", C)
     # decoder forward
     q1, q2 = inv[:nh], inv[nh:]
     hs = hedge[q1] + hedge[q2]
-    dect = x @ W.h("EDEC1N_W", D, C)
+    dect = _fmm(x, W.h("EDEC1N_W", D, C))
     lh, rh = left[q1], right[q1]
-    xh1, rs1 = ln_stats(hs @ W.h("EDEC1_W", C, C) + W.h("EDEC1_B", C) + dect[lh] + dect[rh])
+    xh1, rs1 = ln_stats(_fmm(hs, W.h("EDEC1_W", C, C)) + W.h("EDEC1_B", C) + dect[lh] + dect[rh])
     r1 = torch.relu(xh1 * W.h("EDEC1_G", C) + W.h("EDEC1_BE", C))
-    xh2, rs2 = ln_stats(r1 @ W.h("EDEC2_W", C, C) + W.h("EDEC2_B", C))
+    xh2, rs2 = ln_stats(_fmm(r1, W.h("EDEC2_W", C, C)) + W.h("EDEC2_B", C))
     r2 = torch.relu(xh2 * W.h("EDEC3_G", C) + W.h("EDEC3_BE", C))
-    logits = (r2 @ W.h("EDEC3_W", C, 32) + W.h("EDEC3_B", 32))[:, :ke]
+    logits = (_fmm(r2, W.h("EDEC3_W", C, 32)) + W.h("EDEC3_B", 32))[:, :ke]
     # ---- bwd_decode ----
     dl = torch.zeros(nh, 32)
     dl[:, :ke] = d_logits
@@ -270,43 +297,43 @@ def bondpred_forward_backward(W: Blob, *, num_blocks, rbf_lo, rbf_hi, time_dim, 
         DUL, DUR = scatter(du, left, N), scatter(du, right, N)
         de = du @ W.b(i, "T_EB_SELF", C, C) + dh
         # bwd_edge_nodeblock
-        xh2_, rs2_ = ln_stats(e @ W.b(i, "NB_EN1_W", C, D) + W.b(i, "NB_EN1_B", D))
+        xh2_, rs2_ = ln_stats(_mm(e, W.b(i, "NB_EN1_W", C, D), False) + W.b(i, "NB_EN1_B", D))
         r2_ = torch.relu(xh2_ * W.b(i, "NB_EN1_G", D) + W.b(i, "NB_EN1_BE", D))
-        he = r2_ @ W.b(i, "NB_EN2_W", D, D) + W.b(i, "NB_EN2_B", D)
-        msg = (he * tb["hn"][right]) @ W.b(i, "NB_MSG_W", D, D) + W.b(i, "NB_MSG_B", D)
-        xh3, rs3 = ln_stats(e @ W.b(i, "NB_GE_W", C, D) + tb["gx"][right])
+        he = _mm(r2_, W.b(i, "NB_EN2_W", D, D), False) + W.b(i, "NB_EN2_B", D)
+        msg = _mm((he * tb["hn"][right]), W.b(i, "NB_MSG_W", D, D), False) + W.b(i, "NB_MSG_B", D)
+        xh3, rs3 = ln_stats(_mm(e, W.b(i, "NB_GE_W", C, D), False) + tb["gx"][right])
         r3 = torch.relu(xh3 * W.b(i, "NB_G1_G", D) + W.b(i, "NB_G1_BE", D))
-        sg = torch.sigmoid(r3 @ W.b(i, "NB_G2_W", D, D) + W.b(i, "NB_G2_B", D))
+        sg = torch.sigmoid(_mm(r3, W.b(i, "NB_G2_W", D, D), False) + W.b(i, "NB_G2_B", D))
         dout = dagg[left]
         dgt, dmsg = dout * msg * sg * (1 - sg), dout * sg
-        da3 = ln_relu_bwd(dgt @ W.b(i, "T_NB_G2", D, D), xh3, rs3, W.b(i, "NB_G1_G", D), W.b(i, "NB_G1_BE", D))
+        da3 = ln_relu_bwd(_mm(dgt, W.b(i, "T_NB_G2", D, D), True), xh3, rs3, W.b(i, "NB_G1_G", D), W.b(i, "NB_G1_BE", D))
         dgx = scatter(da3, right, N)
-        de = de + da3 @ W.b(i, "T_NB_GE", D, C)
-        dm = dmsg @ W.b(i, "T_NB_MSG", D, D)
+        de = de + _mm(da3, W.b(i, "T_NB_GE", D, C), True)
+        dm = _mm(dmsg, W.b(i, "T_NB_MSG", D, D), True)
         dhn = scatter(dm * he, right, N)
-        da2 = ln_relu_bwd((dm * tb["hn"][right]) @ W.b(i, "T_NB_EN2", D, D), xh2_, rs2_, W.b(i, "NB_EN1_G", D), W.b(i, "NB_EN1_BE", D))
-        de = de + da2 @ W.b(i, "T_NB_EN1", D, C)
+        da2 = ln_relu_bwd(_mm((dm * tb["hn"][right]), W.b(i, "T_NB_EN2", D, D), True), xh2_, rs2_, W.b(i, "NB_EN1_G", D), W.b(i, "NB_EN1_BE", D))
+        de = de + _mm(da2, W.b(i, "T_NB_EN1", D, C), True)
         # bwd_edge_bondffn
         dnl, dgn = {}, {}
         for s, S, node, other, DU in (("l", "EL", left, right, DUL), ("r", "ER", right, left, DUR)):
-            bl = e @ W.b(i, S + "_BL_W", C, 128)
-            xh5, rs5 = ln_stats((bl * tb["nl" + s][node]) @ W.b(i, S + "_I1_W", 128, 128) + W.b(i, S + "_I1_B", 128))
+            bl = _mm(e, W.b(i, S + "_BL_W", C, 128), False)
+            xh5, rs5 = ln_stats(_mm((bl * tb["nl" + s][node]), W.b(i, S + "_I1_W", 128, 128), False) + W.b(i, S + "_I1_B", 128))
             r5 = torch.relu(xh5 * W.b(i, S + "_I1_G", 128) + W.b(i, S + "_I1_BE", 128))
-            i2 = r5 @ W.b(i, S + "_I2_W", 128, C) + W.b(i, S + "_I2_B", C)
-            xh6, rs6 = ln_stats(e @ W.b(i, S + "_GB_W", C, 32) + tb["gn" + s][node] + te[:, None] * W.b(i, S + "_GT_W", 32))
+            i2 = _mm(r5, W.b(i, S + "_I2_W", 128, C), False) + W.b(i, S + "_I2_B", C)
+            xh6, rs6 = ln_stats(_mm(e, W.b(i, S + "_GB_W", C, 32), False) + tb["gn" + s][node] + te[:, None] * W.b(i, S + "_GT_W", 32))
             r6 = torch.relu(xh6 * W.b(i, S + "_G1_G", 32) + W.b(i, S + "_G1_BE", 32))
-            sgg = torch.sigmoid(r6 @ W.b(i, S + "_G2_W", 32, C) + W.b(i, S + "_G2_B", C))
+            sgg = torch.sigmoid(_mm(r6, W.b(i, S + "_G2_W", 32, C), False) + W.b(i, S + "_G2_B", C))
             do = DU[other]
             dgg, di2 = do * i2 * sgg * (1 - sgg), do * sgg
-            da6 = ln_relu_bwd(dgg @ W.b(i, "T_" + S + "_G2", C, 32), xh6, rs6, W.b(i, S + "_G1_G", 32), W.b(i, S + "_G1_BE", 32))
+            da6 = ln_relu_bwd(_mm(dgg, W.b(i, "T_" + S + "_G2", C, 32), True), xh6, rs6, W.b(i, S + "_G1_G", 32), W.b(i, S + "_G1_BE", 32))
             dgn[s] = scatter(da6, node, N)
-            de = de + da6 @ W.b(i, "T_" + S + "_GB", 32, C)
-            da5 = ln_relu_bwd(di2 @ W.b(i, "T_" + S + "_I2", C, 128), xh5, rs5, W.b(i, S + "_I1_G", 128), W.b(i, S + "_I1_BE", 128))
-            dinter = da5 @ W.b(i, "T_" + S + "_I1", 128, 128)
+            de = de + _mm(da6, W.b(i, "T_" + S + "_GB", 32, C), True)
+            da5 = ln_relu_bwd(_mm(di2, W.b(i, "T_" + S + "_I2", C, 128), True), xh5, rs5, W.b(i, S + "_I1_G", 128), W.b(i, S + "_I1_BE", 128))
+            dinter = _mm(da5, W.b(i, "T_" + S + "_I1", 128, 128), True)
             dnl[s] = scatter(dinter * bl, node, N)
-            de = de + (dinter * tb["nl" + s][node]) @ W.b(i, "T_" + S + "_BL", 128, C)
-        dh = de @ W.b(i, "T_EEH", C, C)
-        dG = dG + (de @ W.b(i, "T_EEG", C, 32))[:, :G]
+            de = de + _mm((dinter * tb["nl" + s][node]), W.b(i, "T_" + S + "_BL", 128, C), True)
+        dh = _mm(de, W.b(i, "T_EEH", C, C), True)
+        dG = dG + _mm(de, W.b(i, "T_EEG", C, 32), True)[:, :G]
         # phase B
         dx = dx + DUL @ W.b(i, "T_EB_NFL", C, D) + DUR @ W.b(i, "T_EB_NFR", C, D)
         dx = dx + dnl["l"] @ W.b(i, "T_EL_NL", 128, D) + dnl["r"] @ W.b(i, "T_ER_NL", 128, D)

@@ -243,6 +243,31 @@ def q_vt_pred(sd, p, log_v0, t, batch, eps=1e-30):
     return torch.log(q + eps).clamp_min(-32.0)
 
 
+def compute_v_Lt(log_post_true, log_post_pred, log_v0, t, batch):
+    """models/transition.py:317-329 with models/diffusion.py:85-91 (categorical_kl, log_categorical) inlined:
+    KL(q(v_{t-1} | v_t, v_0) || p(v_{t-1} | v_t)) per item, the decoder NLL instead for items whose graph sits at t = 0."""
+    kl = (log_post_true.exp() * (log_post_true - log_post_pred)).sum(dim=-1)
+    nll = -(log_v0.exp() * log_post_pred).sum(dim=-1)
+    mask = (t == 0).float()[batch]
+    return mask * nll + (1 - mask) * kl
+
+
+def loss_terms(sd, node_pos, time_step, batch_node, batch_halfedge, pred_node, pred_pos, pred_half,
+               log_node_t, log_node_0, log_half_t, log_half_0):
+    """models/model.py:166-201, discrete categorical space, bond_len_loss off (configs/train/train_MolDiff.yml):
+    MSE on the positions + 100 x mean variational-bound term for atom and bond types."""
+    loss_pos = F.mse_loss(pred_pos, node_pos)
+    terms = {}
+    for key, p, logits, log_t, log_0, batch in (("node", "node_transition", pred_node, log_node_t, log_node_0, batch_node),
+                                                ("edge", "edge_transition", pred_half, log_half_t, log_half_0, batch_halfedge)):
+        log_recon = F.log_softmax(logits, dim=-1)
+        post_true = q_v_posterior(sd, p, log_0, log_t, time_step, batch)
+        post_pred = q_v_posterior(sd, p, log_recon, log_t, time_step, batch)
+        terms[key] = torch.mean(compute_v_Lt(post_true, post_pred, log_0, time_step, batch)) * 100
+    total = loss_pos + terms["node"] + terms["edge"]
+    return {"loss": total, "loss_pos": loss_pos, "loss_node": terms["node"], "loss_edge": terms["edge"]}
+
+
 def index_to_log_onehot(x, k):
     """models/diffusion.py:53-57."""
     return torch.log(F.one_hot(x, k).float().clamp(min=1e-30))

@@ -94,6 +94,52 @@ def test_add_noise_and_get_loss_plumbing(seeded_models, monkeypatch):
     assert h.shape == inp["h_node"].shape and p.shape == inp["pos"].shape and e.shape == inp["h_half"].shape
 
 
+def _clean_molecules(B, seed):
+    """Same synthetic 'dataset' batch as tests/golden/make_golden_loss.py."""
+    import numpy as np
+    np.random.seed(2023 + seed)
+    ph = R.make_data_placeholder(B)
+    g = torch.Generator().manual_seed(seed)
+    n, eh = len(ph["batch_node"]), len(ph["batch_halfedge"])
+    return dict(batch_node=ph["batch_node"], halfedge_index=ph["halfedge_index"], batch_halfedge=ph["batch_halfedge"],
+                node_type=torch.randint(0, 7, (n,), generator=g), halfedge_type=torch.randint(0, 5, (eh,), generator=g),
+                node_pos=torch.randn(n, 3, generator=g) * 2.0)
+
+
+@pytest.mark.parametrize("name", ["B8_seed5", "B24_seed6"])
+def test_get_loss_reproduces_reference(name, golden_loss, seeded_models, monkeypatch):
+    """MolDiff.get_loss (model.py:128-201) with the oracle injected as the denoiser and the reference's seed: the product
+    draws the time steps and the perturbation in the reference's RNG order (bitwise equal to the recorded draws) and
+    returns the reference's four loss values."""
+    md = seeded_models[0]
+    sd = md.state_dict()
+    case = golden_loss[name]
+    seen = {}
+
+    def oracle_forward(self, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t):
+        seen.update(h_node=h_node_pert, pos=pos_pert, t=t, h_edge=h_edge_pert)
+        with torch.no_grad():
+            return R.moldiff_forward(sd, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t)
+
+    monkeypatch.setattr(type(md), "forward", oracle_forward)
+    mol = _clean_molecules(case["args"]["B"], case["args"]["seed"])
+    torch.manual_seed(case["torch_seed"])
+    out = md.get_loss(mol["node_type"], mol["node_pos"], mol["batch_node"], mol["halfedge_type"], mol["halfedge_index"],
+                      mol["batch_halfedge"], case["args"]["B"])
+    assert torch.equal(seen["t"], case["time_step"]) and torch.equal(seen["pos"], case["pos_pert"])
+    assert torch.equal(seen["h_node"], case["h_node_pert"])
+    assert torch.equal(seen["h_edge"], torch.cat([case["h_half_pert"], case["h_half_pert"]], 0))
+    for k, v in case["losses"].items():
+        assert abs(float(out[k]) - v) <= 1e-6 * abs(v), (k, float(out[k]), v)
+    # the oracle's restatement of the loss arithmetic on the recorded reference predictions
+    pr = case["preds"]
+    mine = R.loss_terms(sd, mol["node_pos"], case["time_step"], mol["batch_node"], mol["batch_halfedge"], pr["pred_node"],
+                        pr["pred_pos"], pr["pred_halfedge"], case["log_node_t"], case["log_node_0"], case["log_half_t"],
+                        case["log_half_0"])
+    for k, v in case["losses"].items():
+        assert abs(float(mine[k]) - v) <= 1e-6 * abs(v), (k, float(mine[k]), v)
+
+
 def test_sampler_loop_reproduces_reference_trajectory(golden, monkeypatch):
     """With the oracle injected as the denoiser and the same seeds, MolDiff.sample consumes the RNG in the same
     order as the reference and so reproduces its 50-step CPU trajectory (final state and last predictions)."""
