@@ -117,7 +117,11 @@ enum mdb_head_slot {
   X(BT_ER_G2) X(BT_ER_I2) X(BT_ER_GB) X(BT_ER_I1) X(BT_ER_BL)                                      \
   /* per-node Linears (tc_node_kernel): NodeBlock node path, PosUpdate node MLPs, hoisted projections */ \
   X(NB_OUT) X(PU_LL1) X(PU_LL2) X(PU_RL1) X(PU_RL2) X(NB_NN1) X(NB_NN2) X(NB_GX) X(NB_CEN)         \
-  X(EL_NL) X(ER_NL) X(EL_GN) X(ER_GN) X(EB_NFL) X(EB_NFR)
+  X(EL_NL) X(ER_NL) X(EL_GN) X(ER_GN) X(EB_NFL) X(EB_NFR)                                          \
+  /* transposed use in the tensor-core backward of the EdgeBlock tail and of the per-node path (bond predictor only) */ \
+  X(BT_EB_OUT) X(BT_EB_SELF)                                                                       \
+  X(BT_EB_NFL) X(BT_EB_NFR) X(BT_EL_NL) X(BT_ER_NL) X(BT_EL_GN) X(BT_ER_GN)                        \
+  X(BT_NB_GX) X(BT_NB_NN2) X(BT_NB_NN1) X(BT_NB_OUT) X(BT_NB_CEN)
 
 enum mdb_tc_slot {
 #define MDB_X(name) MDB_T_##name,
@@ -127,7 +131,7 @@ enum mdb_tc_slot {
 };
 
 /* Tensor-core images of the head Linears applied per node (decoders). */
-#define MDB_TC_HEAD_SLOTS(X) X(NDEC1) X(NDEC2) X(EDEC1N)
+#define MDB_TC_HEAD_SLOTS(X) X(NDEC1) X(NDEC2) X(EDEC1N) X(BT_EDEC1N)
 
 enum mdb_tc_head_slot {
 #define MDB_X(name) MDB_TH_##name,
@@ -214,7 +218,8 @@ int mdb_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan,
 #define MDB_KERNEL_CLASSES(X)                                                                      \
   X(node_init) X(edge_init) X(node) X(edge_b) X(edge_d) X(edge_decode) X(edge_unsort)              \
   X(bwd_decode) X(bwd_node) X(bwd_edge_tail) X(bwd_edge_nodeblock) X(bwd_edge_bondffn) X(bwd_pos)   \
-  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition) X(graph_build) X(decode_rows)
+  X(tc_nodeblock) X(tc_nodeblock_bwd) X(tc_edge_d) X(tc_bondffn) X(tc_bondffn_bwd) X(tc_node) X(transition) X(graph_build) X(decode_rows) \
+  X(tc_edge_tail_bwd) X(tc_node_bwd)
 
 enum mdb_kernel_class {
 #define MDB_X(name) MDB_K_##name,

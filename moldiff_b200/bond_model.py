@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import engine
+from . import engine, train_path
 from .diffusion_model import _PackedMixin, build_transitions
 from .nets import MLP, GaussianSmearing, NodeEdgeNet
 
@@ -25,14 +25,15 @@ class _BondLogits(torch.autograd.Function):
         net = module._packed_net(pos.device)
         need_grad = pos.requires_grad
         logits = engine.bondpred_forward(net, plan, h_node, pos, batch_node, batch_edge, t, save=need_grad)
-        ctx.net, ctx.plan = net, plan
+        ctx.net, ctx.plan, ctx.generation = net, plan, plan.save_generation
         ctx.save_for_backward(h_node, pos, batch_node, batch_edge, t)
         return logits
 
     @staticmethod
     def backward(ctx, grad_logits):
         h_node, pos, batch_node, batch_edge, t = ctx.saved_tensors
-        d_pos = engine.bondpred_backward(ctx.net, ctx.plan, h_node, pos, batch_node, batch_edge, t, grad_logits)
+        d_pos = engine.bondpred_backward(ctx.net, ctx.plan, h_node, pos, batch_node, batch_edge, t, grad_logits,
+                                         generation=ctx.generation)
         return d_pos, None, None, None, None, None, None
 
 
@@ -77,6 +78,15 @@ class BondPredictor(nn.Module, _PackedMixin):
         """Bond-type logits for the half edges, [E/2, num_edge_types] (bond_predictor.py:128-162)."""
         if self.num_timesteps == 0:
             t = torch.zeros(int(batch_node.max()) + 1, device=pos_node.device, dtype=torch.long)
+        if train_path.needs_training_backward(self):          # train_bond.py: weight gradients (fused forward, recompute-in-backward)
+            plan = engine.plan_for(edge_index, h_node.shape[0])
+
+            def fused(hn, ps):
+                return engine.bondpred_forward(self._packed_net(ps.device), plan, hn, ps, batch_node, batch_edge, t)
+
+            def recompute(hn, ps):
+                return train_path.bondpred_forward(self, hn, ps, batch_node, edge_index, batch_edge, t)
+            return train_path.RecomputeBackward.apply(fused, recompute, 2, h_node.float(), pos_node.float(), *self.parameters())
         return _BondLogits.apply(pos_node, self, h_node, batch_node, edge_index, batch_edge, t)
 
     def get_loss(self, node_type, node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge, num_mol):

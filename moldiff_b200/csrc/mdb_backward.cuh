@@ -703,8 +703,10 @@ constexpr size_t SMEM_BWD_NB = (TM * C + 2 * TM * D + 2 * WCHUNK + 3 * TM) * siz
 constexpr size_t SMEM_BWD_FFN = (2 * TM * C + 2 * TM * 128 + 2 * WCHUNK + 3 * TM) * sizeof(float);
 
 int ensure_bwd_attrs() {
-  static bool done = false;
-  if (done) return MDB_OK;
+  static bool done[64] = {};
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return MDB_OK;
   CUDA_TRY(cudaFuncSetAttribute(bwd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_DEC));
   CUDA_TRY(cudaFuncSetAttribute(bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_NODE));
   CUDA_TRY(cudaFuncSetAttribute(bwd_edge_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD_TAIL));
@@ -713,7 +715,8 @@ int ensure_bwd_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD16));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD));
-  done = true;
+  CUDA_TRY(cudaFuncSetAttribute(tc_edge_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_TAIL_BWD));
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return MDB_OK;
 }
 
@@ -797,7 +800,20 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
     fill_blk(ea.off, net, i);
     ea.tb = tbi;
     ea.e = sv.e + (size_t)i * EC; ea.sl = sv.slsr + (size_t)i * 2 * NC; ea.fl = tbi.fl; ea.fr = tbi.fr;
-    LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
+    static const bool tc_tail_env = []() { const char* e = getenv("MDB_TC_TAIL_BWD"); return e == nullptr || e[0] != '0'; }();
+    if (tc_tail_env && net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[i][MDB_T_BT_EB_OUT] >= 0) {
+      TcEdgeTailBwdArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob);
+      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
+      ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
+      ta.e = ea.e; ta.dh = sv.dh; ta.sl = ea.sl; ta.fl = ea.fl; ta.fr = ea.fr; ta.dul = sv.dul; ta.dur = sv.dur; ta.de = sv.de;
+      fill_edge_tail_bwd_vecs(ta.v, net->blob_host, ea.off);
+      LAUNCH(MDB_K_tc_edge_tail_bwd, st,
+             (tc_edge_tail_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_TAIL_BWD, st>>>(ta)));
+    } else {
+      LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
+    }
     if (nb_tc(i)) {
       if (bwd16_env) {
         TcNbBwd16Args ta;

@@ -680,6 +680,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_nodeblock16.cuh"
 #include "tc_nodeblock_bwd16.cuh"
 #include "tc_node.cuh"
+#include "tc_edge_tail_bwd.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -803,10 +804,10 @@ constexpr size_t SMEM_EDGE_D = (3 * TM * C + TM * D + 2 * WCHUNK + TM + 4 * TM +
 constexpr size_t SMEM_DEC = (2 * TM * C + 2 * WCHUNK + 2 * TM) * sizeof(float);
 
 int ensure_attrs() {
-  static bool done = false;
-  if (done) return MDB_OK;
+  static bool done[64] = {};       // per device: the max-dynamic-smem attribute is a property of (function, device)
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[dev]) return MDB_OK;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail(MDB_EARCH, "moldiff_b200 kernels are built for sm_100a only%s");
@@ -823,7 +824,7 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
   CUDA_TRY(cudaFuncSetAttribute(tc_node_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NODE));
   CUDA_TRY(cudaFuncSetAttribute(tc_node_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NODE));
-  done = true;
+  if (dev >= 0 && dev < 64) done[dev] = true;
   return MDB_OK;
 }
 
@@ -849,7 +850,13 @@ bool cross_first(const mdb_net_desc* net) {
 
 // node kernel launch: tensor-core version when its operand images are packed, FFMA version otherwise
 int launch_node(const mdb_net_desc* net, const NodeArgs& na, int blk_mid, int blk_pre, int node_tiles, cudaStream_t st) {
-  static const bool tc_node_on = []() { const char* e = getenv("MDB_TC_NODE"); return e == nullptr || e[0] != '0'; }();
+  // Per-node tables are gathered by every edge of the node, so an error in them is COHERENT over ~25 edges instead of averaging
+  // out: with the bond predictor's node path on tensor cores the guidance gradient sits at 4e-5..6e-5 of fp64 (crossed-path
+  // runs, profiles/r02_tc_numerics.txt), on the fp32 FFMA node kernel at 5e-6 -- so the bond predictor (kind 2) takes the
+  // FFMA node kernel (N rows only: ~10 % of its forward) and the denoiser the tensor-core one.  MDB_TC_NODE=0 / 1 forces
+  // FFMA / tensor cores for every network (A/B runs).
+  static const int tc_node_env = []() { const char* e = getenv("MDB_TC_NODE"); return e == nullptr ? -1 : (e[0] != '0' ? 1 : 0); }();
+  const bool tc_node_on = tc_node_env >= 0 ? tc_node_env == 1 : net->kind != 2;
   const int ref_blk = blk_pre >= 0 ? blk_pre : blk_mid;
   const bool tc = tc_node_on && net->tc_blob != nullptr && net->blob_host != nullptr && ref_blk >= 0 &&
                   net->tc_block_off[ref_blk][MDB_T_NB_OUT] >= 0;

@@ -18,6 +18,10 @@ from . import engine
 
 
 def _offsets(batch, n_items, n_graphs):
+    # contiguous per-molecule segments are what makes the offset split valid (the reference's boolean masks accept any order)
+    if batch.numel() > 1 and bool((batch[1:] < batch[:-1]).any()):
+        raise engine.MoldiffB200Error("decode_batch needs batch vectors sorted by molecule (as make_data_placeholder / "
+                                      "the PyG loader produce them)")
     counts = torch.bincount(batch, minlength=n_graphs)
     off = np.zeros(n_graphs + 1, dtype=np.int64)
     off[1:] = np.cumsum(counts.cpu().numpy())

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import engine
+from . import engine, train_path
 from .nets import MLP, GaussianSmearing, NodeEdgeNet
 from .schedules import get_beta_schedule
 from .transitions import CategoricalTransition, GaussianTransition, gumbel_argmax
@@ -119,11 +119,21 @@ class MolDiff(nn.Module, _PackedMixin):
         return [node_pert[0], pos_pert, half_pert[0]]
 
     def forward(self, h_node_pert, pos_pert, batch_node, h_edge_pert, edge_index, batch_edge, t):
-        """Predict the clean molecule from its perturbed version at step t (model.py:204-234)."""
+        """Predict the clean molecule from its perturbed version at step t (model.py:204-234).  One C-ABI call; in a training
+        step (train() mode with autograd recording) the same call is wrapped so that `loss.backward()` reaches the parameters
+        (train_path.RecomputeBackward: fused forward, recompute-in-backward)."""
         plan = engine.plan_for(edge_index, h_node_pert.shape[0])
-        net = self._packed_net(pos_pert.device)
-        pred_node, pred_pos, pred_half = engine.moldiff_forward(
-            net, plan, h_node_pert, pos_pert, h_edge_pert, batch_node, batch_edge, t)
+
+        def fused(hn, ps, he):
+            return engine.moldiff_forward(self._packed_net(ps.device), plan, hn, ps, he, batch_node, batch_edge, t)
+
+        if train_path.needs_training_backward(self):
+            def recompute(hn, ps, he):
+                return train_path.moldiff_forward(self, hn, ps, batch_node, he, edge_index, batch_edge, t)
+            pred_node, pred_pos, pred_half = train_path.RecomputeBackward.apply(
+                fused, recompute, 3, h_node_pert.float(), pos_pert.float(), h_edge_pert.float(), *self.parameters())
+        else:
+            pred_node, pred_pos, pred_half = fused(h_node_pert, pos_pert, h_edge_pert)
         return {"pred_node": pred_node, "pred_pos": pred_pos, "pred_halfedge": pred_half}
 
     def get_loss(self, node_type, node_pos, batch_node, halfedge_type, halfedge_index, batch_halfedge, num_mol):
@@ -238,7 +248,10 @@ class MolDiff(nn.Module, _PackedMixin):
         discrete = self.categorical_space == "discrete"
         batch_node, batch_halfedge = st["batch_node"], st["batch_halfedge"]
         h_node, pos, h_half = st["h_node"], st["pos"], st["h_half"]
-        time_step = torch.full((st["n_graphs"],), step, dtype=torch.long, device=device)
+        if torch.is_tensor(step):      # a device tensor [n_graphs] (CUDA-graphed step: the value changes between replays)
+            time_step = step
+        else:
+            time_step = torch.full((st["n_graphs"],), step, dtype=torch.long, device=device)
         h_edge = st.pop("h_edge2", None)              # [2 Eh, Ke] written directly by the fused transition step
         if h_edge is None or h_edge.data_ptr() != h_half.data_ptr():   # (stale if the caller replaced st["h_half"])
             h_edge = torch.cat([h_half, h_half], dim=0)
@@ -280,6 +293,12 @@ class MolDiff(nn.Module, _PackedMixin):
         st["h_node"], st["pos"], st["h_half"] = h_node_prev, pos_prev, h_half_prev
         return preds
 
+    def graphed_step(self, st, bond_predictor=None, guidance=None):
+        """CUDA-graph capture of one loop body: returns `GraphedStep`, whose `run(step)` replays the ~50
+        (unguided) / ~110 (guided) kernel launches of `sample_step` as ONE graph launch -- at config-1 size (B = 32) the step
+        is launch-bound.  The sampler state lives in static buffers owned by the returned object."""
+        return GraphedStep(self, st, bond_predictor, guidance)
+
     @torch.no_grad()
     def sample(self, n_graphs, batch_node, halfedge_index, batch_halfedge, bond_predictor=None, guidance=None,
                progress=False):
@@ -298,8 +317,69 @@ class MolDiff(nn.Module, _PackedMixin):
             from tqdm import tqdm
             steps = tqdm(steps, total=T)
         preds = None
+        graphed = None
+        if getattr(self, "cuda_graph", False) and device.type == "cuda":
+            graphed = self.graphed_step(st, bond_predictor=bond_predictor, guidance=guidance)
+            st = graphed.st
         for i, step in enumerate(steps):
-            preds = self.sample_step(st, step, bond_predictor=bond_predictor, guidance=guidance)
+            if graphed is not None:
+                preds = graphed.run(step)
+            else:
+                preds = self.sample_step(st, step, bond_predictor=bond_predictor, guidance=guidance)
             node_traj[i + 1], pos_traj[i + 1], half_traj[i + 1] = st["h_node"], st["pos"], st["h_half"]
         return {"pred": [preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]],
                 "traj": [node_traj, pos_traj, half_traj]}
+
+
+class GraphedStep:
+    """One body of the reverse-diffusion loop (`MolDiff.sample_step`: denoiser, fused posterior sampling, optional bond-
+    predictor guidance forward + backward) captured once as a CUDA graph and replayed per time step.  Everything the body
+    reads or writes between steps is a static buffer: the sampler state (`self.st`), the time-step vector and the last
+    predictions; the random variates come from torch's graph-safe Philox state.  Discrete space + fused transition only."""
+
+    STATE = ("h_node", "pos", "log_node", "log_half")
+
+    def __init__(self, model, st, bond_predictor=None, guidance=None, warmup=2):
+        dev = st["pos"].device
+        if dev.type != "cuda" or model.categorical_space != "discrete" or not model.fused_transition:
+            raise engine.MoldiffB200Error("GraphedStep needs CUDA tensors, the discrete space and the fused transition step")
+        self.model, self.bond, self.guidance = model, bond_predictor, guidance
+        n_half = st["h_half"].shape[0]
+        self.st = dict(st)
+        for k in self.STATE:
+            self.st[k] = st[k].clone()
+        self.h_edge2 = torch.cat([st["h_half"], st["h_half"]], dim=0)      # [2 Eh, Ke]; st["h_half"] is its first half
+        self.st["h_half"] = self.h_edge2[:n_half]
+        self.t = torch.zeros(st["n_graphs"], dtype=torch.long, device=dev)
+        saved = {k: self.st[k].clone() for k in self.STATE}
+        saved_edge = self.h_edge2.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                 # warm-up on a side stream: lazy initialisation, plan, workspaces, packing
+            self.t.fill_(model.num_timesteps - 1)
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = engine.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.preds = self._body()
+        self.launches_per_replay = engine.launch_count() - n0     # kernels of this library inside one replay
+        for k in self.STATE:                          # the warm-up steps advanced the chain: rewind
+            self.st[k].copy_(saved[k])
+        self.h_edge2.copy_(saved_edge)
+
+    @torch.no_grad()
+    def _body(self):
+        work = dict(self.st)
+        work["h_edge2"] = self.h_edge2
+        preds = self.model.sample_step(work, self.t, bond_predictor=self.bond, guidance=self.guidance)
+        for k in self.STATE:
+            self.st[k].copy_(work[k])
+        self.h_edge2.copy_(work["h_edge2"])
+        return preds
+
+    def run(self, step):
+        self.t.fill_(int(step))
+        self.graph.replay()
+        return self.preds

@@ -6,6 +6,7 @@ CUDA device, every entry point raises.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 import threading
@@ -140,6 +141,21 @@ KERNEL_LOGICAL_FLOP_PER_EDGE = {
 }
 
 
+# The GEMMs each tensor-core kernel EXECUTES per 128-edge tile after per-node hoisting, as (K, N) -- one logical GEMM = 3 MMAs per
+# K step (hi*hi + lo*hi + hi*lo).  Executed MMA FLOP per edge = 3 * 2 * sum(K * N)  (roofline.achieved).
+_FFN = [(64, 128), (64, 32), (128, 128), (32, 64), (128, 64)]                  # one BondFFN: bond_linear, gate.0, inter.0, gate.3, inter.3
+KERNEL_GEMMS = {
+    "tc_nodeblock": [(64, 256), (256, 256), (256, 256), (64, 256), (256, 256)],   # edge_net.0/.3, msg_net, gate.0 (edge part), gate.3
+    # forward recompute (5, gate.0 edge part twice more for the two LN backwards -> counted below) + 7 backward GEMMs
+    "tc_nodeblock_bwd": [(64, 256), (256, 256), (256, 256), (64, 256), (256, 256),
+                         (256, 256), (64, 256), (256, 64), (256, 256), (256, 256), (64, 256), (256, 64)],
+    "tc_bondffn": [(80, 64)] + _FFN + _FFN,
+    "tc_bondffn_bwd": (_FFN + [(64, 32), (64, 128), (32, 64), (128, 128), (128, 64)]) * 2 + [(64, 64), (64, 32)],
+    "tc_edge_d": [(64, 64), (64, 64), (64, 256), (64, 256), (256, 256), (64, 32), (64, 32)],   # denoiser (with PosUpdate)
+}
+KERNEL_MMA_FLOP_PER_EDGE = {k: 3 * 2.0 * sum(a * b for a, b in v) for k, v in KERNEL_GEMMS.items()}
+
+
 def profile_kernels(fn, reps=1):
     """Run fn() `reps` times with per-kernel CUDA-event timing enabled; returns {class: {ms_total, launches}}."""
     lib = load_library()
@@ -262,30 +278,39 @@ class GraphPlan:
         p.perm, p.inv = self.perm.data_ptr(), self.inv.data_ptr()
         self.c = p
         self._workspace = {}
+        self.save_generation = 0     # bumped by every bondpred_forward(save=True): the saved activations live in the workspace
 
     def workspace(self, with_backward, num_blocks):
         key = (int(with_backward), int(num_blocks))
         ws = self._workspace.get(key)
         if ws is None:
             nbytes = load_library().mdb_workspace_bytes(self.n_nodes, self.n_edges, key[0], key[1])
-            # zero-filled once: several accumulators in the workspace are "left zero by the previous call"
+            # Contract: every accumulator inside the workspace is cleared INSIDE the call that uses it (memsets at the head of
+            # run_forward / run_bondpred_backward, the node kernels re-arm the per-block ones), so a call never depends on what
+            # the previous one left behind -- tests/test_gpu_parity.py poisons the workspace with NaNs to hold that.  The
+            # zero fill only keeps never-read padding rows (node-blocked tables) finite.
             ws = torch.zeros((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
             self._workspace[key] = ws
         return ws
 
 
-_plan_cache = {}
+_plan_cache = collections.OrderedDict()
+PLAN_CACHE_SIZE = 4        # batches whose plan (sorted edge list + workspaces) stays alive; a training loop alternates a few
 
 
 def plan_for(edge_index, n_nodes):
     """Plans are cached on the identity + version of the edge_index tensor: MolDiff.sample reuses one
-    edge_index for all T steps, so the sort runs once per batch."""
+    edge_index for all T steps, so the sort runs once per batch.  Small LRU: interleaved batches (train / validation,
+    guided sampling of two batch sizes) keep their plans instead of re-sorting on every call."""
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(n_nodes), str(edge_index.device))
-    hit = _plan_cache.get("k")
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    hit = _plan_cache.get(key)
+    if hit is not None:
+        _plan_cache.move_to_end(key)
+        return hit[0]
     plan = GraphPlan(edge_index, n_nodes)
-    _plan_cache["k"] = (key, plan, edge_index)   # keep edge_index alive so data_ptr cannot be recycled
+    _plan_cache[key] = (plan, edge_index)        # keep edge_index alive so data_ptr cannot be recycled
+    while len(_plan_cache) > PLAN_CACHE_SIZE:
+        _plan_cache.popitem(last=False)
     return plan
 
 
@@ -331,10 +356,11 @@ def moldiff_forward(net: PackedNet, plan: GraphPlan, h_node_pert, pos_pert, h_ed
 
 
 def transition_step(pos_tr, node_tr, edge_tr, t, batch_node, batch_half, pos, pred_pos, pred_node, log_node,
-                    pred_half, log_half):
+                    pred_half, log_half, noise=None):
     """One fused reverse-transition step of the sampler (`mdb_transition_step`): Gaussian posterior for the positions,
     categorical posteriors + Gumbel-max for node / half-edge types.  The random variates are drawn here from torch's
     generator in the order the unfused PyTorch path consumes them (positions, node types, half-edge types).
+    `noise` = (z_pos ~ N(0,1) [N,3], u_node ~ U[0,1) [N,Kn], u_half ~ U[0,1) [Eh,Ke]) replaces the draws (parity tests).
     Returns (pos_prev, log_node, h_node_prev, log_half, h_edge_prev [2 Eh, Ke], half_type_prev [Eh])."""
     lib = load_library()
     pos, pred_pos = _dev_f32(pos, "pos"), _dev_f32(pred_pos, "pred_pos")
@@ -346,9 +372,14 @@ def transition_step(pos_tr, node_tr, edge_tr, t, batch_node, batch_half, pos, pr
     if kn != node_tr.num_classes or ke != edge_tr.num_classes or kn > 16 or ke > 16:
         raise MoldiffB200Error("transition_step: class counts do not match the transitions (or exceed 16)")
     dev = pos.device
-    z_pos = torch.randn_like(pos)
-    u_node = torch.rand_like(pred_node)
-    u_half = torch.rand_like(pred_half)
+    if noise is None:
+        z_pos = torch.randn_like(pos)
+        u_node = torch.rand_like(pred_node)
+        u_half = torch.rand_like(pred_half)
+    else:
+        z_pos, u_node, u_half = (_dev_f32(x, "noise") for x in noise)
+        if z_pos.shape != pos.shape or u_node.shape != pred_node.shape or u_half.shape != pred_half.shape:
+            raise MoldiffB200Error("transition_step: noise shapes do not match the state")
     pos_out = torch.empty_like(pos)
     log_node_out, h_node_out = torch.empty_like(log_node), torch.empty_like(log_node)
     log_half_out = torch.empty_like(log_half)
@@ -376,6 +407,8 @@ def bondpred_forward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, b
         raise MoldiffB200Error("BondPredictor.forward: input shapes do not match the graph plan / type counts")
     logits = torch.empty(E // 2, net.desc.num_edge_types, dtype=torch.float32, device=pos.device)
     ws = plan.workspace(1 if save else 0, net.num_blocks)
+    if save:
+        plan.save_generation += 1
     rc = lib.mdb_bondpred_forward(C.byref(net.desc), C.byref(plan.c), h_node.data_ptr(), pos.data_ptr(),
                                   batch_node.data_ptr(), batch_edge.data_ptr(), t.data_ptr(), logits.data_ptr(),
                                   1 if save else 0, ws.data_ptr(), ws.numel() * 4, _stream_ptr(pos.device))
@@ -383,10 +416,15 @@ def bondpred_forward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, b
     return logits
 
 
-def bondpred_backward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, batch_edge, t, d_logits):
+def bondpred_backward(net: PackedNet, plan: GraphPlan, h_node, pos, batch_node, batch_edge, t, d_logits, generation=None):
     """d(sum(logits * d_logits)) / d pos through the bond predictor (hand-written backward kernels).  Must
-    follow bondpred_forward(save=True) with the same inputs (the autograd.Function guarantees it)."""
+    follow bondpred_forward(save=True) with the same inputs: the saved activations live in the plan's workspace.  `generation`
+    = plan.save_generation right after that forward; a later save-forward on the same plan has overwritten them and the call
+    raises instead of returning the gradient of the wrong inputs."""
     lib = load_library()
+    if generation is not None and generation != plan.save_generation:
+        raise MoldiffB200Error("bondpred_backward: the activations saved by this forward were overwritten by a later "
+                               "BondPredictor forward on the same graph (one backward per forward, in order)")
     h_node, pos = _dev_f32(h_node, "h_node"), _dev_f32(pos, "pos_node")
     d_logits = _dev_f32(d_logits, "d_logits")
     batch_node, batch_edge, t = _dev_i64(batch_node, "batch_node"), _dev_i64(batch_edge, "batch_edge"), _dev_i64(t, "t")

@@ -348,6 +348,17 @@ def tc_block_tensors(sd, net_prefix, i, update_pos, with_backward):
             o[f"BT_{tag}_GB"] = _asis(gw[:, :EDGE_DIM])                        # [32][64]
             o[f"BT_{tag}_I1"] = _asis(sd[p + ".inter_module.net.0.weight"])    # [128][128]
             o[f"BT_{tag}_BL"] = _asis(sd[p + ".bond_linear.weight"])           # [128][64]
+            o[f"BT_{tag}_NL"] = _asis(sd[p + ".node_linear.weight"])           # [128][256]
+            o[f"BT_{tag}_GN"] = _asis(gw[:, EDGE_DIM:EDGE_DIM + NODE_DIM])     # [32][256]
+        o["BT_EB_OUT"] = _asis(sd[eb + ".out_transform.weight"])               # [64][64]
+        o["BT_EB_SELF"] = _asis(sd[eb + ".self_ffn.weight"])
+        o["BT_EB_NFL"] = _asis(sd[eb + ".node_ffn_left.weight"])               # [64][256]
+        o["BT_EB_NFR"] = _asis(sd[eb + ".node_ffn_right.weight"])
+        o["BT_NB_GX"] = _asis(g0[:, EDGE_DIM:EDGE_DIM + NODE_DIM])             # [256][256]
+        o["BT_NB_NN2"] = _asis(sd[nb + ".node_net.net.3.weight"])
+        o["BT_NB_NN1"] = _asis(sd[nb + ".node_net.net.0.weight"])
+        o["BT_NB_OUT"] = _asis(sd[nb + ".out_transform.weight"])
+        o["BT_NB_CEN"] = _asis(sd[nb + ".centroid_lin.weight"])
     if update_pos:
         pb = f"{net_prefix}.pos_blocks.{i}.edge_lin"
         o["PU_PB"] = _t(sd[pb + ".bond_linear.weight"])        # [64][256]
@@ -364,7 +375,8 @@ def tc_head_tensors(sd, kind):
         return {"NDEC1": _t(sd["node_decoder.net.0.weight"]),
                 "NDEC2": _pad_cols(_t(sd["node_decoder.net.3.weight"]), 32)}
     if kind == 2:
-        return {"EDEC1N": _t(sd["edge_decoder.net.0.weight"][:, EDGE_DIM:])}       # [256][64]
+        return {"EDEC1N": _t(sd["edge_decoder.net.0.weight"][:, EDGE_DIM:]),       # [256][64]
+                "BT_EDEC1N": _asis(sd["edge_decoder.net.0.weight"][:, EDGE_DIM:])}  # [64][256]  (backward: dx = ddect W)
     return {}
 
 

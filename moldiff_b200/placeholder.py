@@ -14,8 +14,21 @@ GEOM_DRUGS_MEAN_ATOMS = 24.923464980477522
 GEOM_DRUGS_STD_ATOMS = 5.516291901819105
 
 
-def make_data_placeholder(n_graphs, device=None, max_size=None):
+def draw_sizes(n_graphs, max_size=None):
+    """The atom counts `make_data_placeholder` would draw (same RNG consumption)."""
     if max_size is None:
+        sizes = np.random.normal(GEOM_DRUGS_MEAN_ATOMS, GEOM_DRUGS_STD_ATOMS, size=n_graphs)
+    else:
+        sizes = np.array([max_size] * n_graphs)
+    return sizes.astype("int64")
+
+
+def make_data_placeholder(n_graphs, device=None, max_size=None, sizes=None):
+    """`sizes` (extension): explicit atom counts, e.g. one rank's share of a batch (sharding.balanced_shards)."""
+    if sizes is not None:
+        sizes = np.asarray(sizes)
+        n_graphs = len(sizes)
+    elif max_size is None:
         sizes = np.random.normal(GEOM_DRUGS_MEAN_ATOMS, GEOM_DRUGS_STD_ATOMS, size=n_graphs)
     else:
         sizes = np.array([max_size] * n_graphs)

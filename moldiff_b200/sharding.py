@@ -22,6 +22,21 @@ def shard_range(n_graphs, rank, world_size):
     return start, start + sizes[rank]
 
 
+def balanced_shards(sizes, world_size):
+    """Strong-scaling split of ONE batch: molecule indices per rank such that sum n^2 (the per-edge work, ~FLOPs) is balanced,
+    not the molecule count.  Longest-processing-time greedy: molecules by decreasing n^2, each to the least-loaded rank
+    (load within 4/3 of optimal; within ~1 % for hundreds of molecules).  Indices inside a shard keep the batch order."""
+    import numpy as np
+    sizes = np.asarray(sizes, dtype=np.int64)
+    load = np.zeros(world_size, dtype=np.int64)
+    shards = [[] for _ in range(world_size)]
+    for m in np.argsort(-(sizes * sizes), kind="stable"):
+        r = int(np.argmin(load))
+        shards[r].append(int(m))
+        load[r] += int(sizes[m]) ** 2
+    return [np.array(sorted(s), dtype=np.int64) for s in shards]
+
+
 def gather_predictions(pred, batch_node, batch_halfedge, dist, dst=0):
     """pred = [pred_node [N_r, Kn], pred_pos [N_r, 3], pred_halfedge [Eh_r, Ke]] of this rank's molecules.
     Returns on rank `dst` the concatenation over ranks (molecule ids renumbered globally), None elsewhere."""

@@ -48,3 +48,8 @@ def test_decode_rejects_cpu_and_bad_batches():
     ph, pred_node, pred_pos, pred_half = _batch(3, seed=1)
     with pytest.raises(engine.MoldiffB200Error):
         decode_batch(pred_node, pred_pos, pred_half, 3, ph["batch_node"], ph["halfedge_index"], ph["batch_halfedge"])
+    dev = torch.device("cuda:0")
+    perm = torch.randperm(len(ph["batch_node"]), generator=torch.Generator().manual_seed(0))
+    with pytest.raises(engine.MoldiffB200Error):      # rows not grouped by molecule: the offset split would be wrong
+        decode_batch(pred_node.to(dev), pred_pos.to(dev), pred_half.to(dev), 3, ph["batch_node"][perm].to(dev),
+                     ph["halfedge_index"].to(dev), ph["batch_halfedge"].to(dev))

@@ -312,3 +312,42 @@ def test_new_ops_refuse_cpu_tensors():
     he = torch.triu_indices(5, 5, 1)
     with pytest.raises(engine.MoldiffB200Error):
         decode_batch(torch.randn(5, 8), pos, torch.randn(10, 6), 1, b, he, torch.zeros(10, dtype=torch.long))
+
+
+def test_train_path_equals_oracle_autograd_fp64():
+    """Row N2: the recompute graph that MolDiff / BondPredictor differentiate in a training step (moldiff_b200/train_path.py,
+    the kernels' hoisted dataflow in PyTorch operators) against autograd through the as-written oracle, in float64: outputs and
+    EVERY parameter gradient agree to 1e-10 (the two are the same function; fp32 differs by summation order only)."""
+    from moldiff_b200 import BondPredictor, MolDiff, train_path
+    from moldiff_b200.config import builtin_config
+    inp = batch_inputs(B=3, t_values=(999, 400, 0), pos_scale=1.5)
+    ei, be, he = doubled(inp)
+    dt = torch.float64
+    g = torch.Generator().manual_seed(1)
+    for which in ("moldiff", "bondpred"):
+        torch.manual_seed(0)
+        if which == "moldiff":
+            m = MolDiff(builtin_config("train/train_MolDiff.yml").model, 8, 6).to(dt)
+            out = train_path.moldiff_forward(m, inp["h_node"].to(dt), inp["pos"].to(dt), inp["batch_node"], he.to(dt), ei, be, inp["t"])
+        else:
+            m = BondPredictor(builtin_config("train/train_bondpred.yml").model, 8, 5).to(dt)
+            out = [train_path.bondpred_forward(m, inp["h_node"].to(dt), inp["pos"].to(dt), inp["batch_node"], ei, be, inp["t"])]
+        sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+        if which == "moldiff":
+            r = R.moldiff_forward(sd, inp["h_node"].to(dt), inp["pos"].to(dt), inp["batch_node"], he.to(dt), ei, be, inp["t"])
+            ref = [r["pred_node"], r["pred_pos"], r["pred_halfedge"]]
+        else:
+            ref = [R.bondpred_forward(sd, inp["h_node"].to(dt), inp["pos"].to(dt), inp["batch_node"], ei, be, inp["t"])]
+        w = [torch.randn(a.shape, generator=g).to(dt) for a in out]
+        for a, b in zip(out, ref):
+            assert R.rel_err(a.detach(), b.detach()) < 1e-12
+        sum((a * b).sum() for a, b in zip(out, w)).backward()
+        sum((a * b).sum() for a, b in zip(ref, w)).backward()
+        n_checked = 0
+        for name, p in m.named_parameters():
+            if not p.requires_grad:
+                continue
+            assert p.grad is not None and sd[name].grad is not None, name
+            assert R.rel_err(p.grad, sd[name].grad) < 1e-10, name
+            n_checked += 1
+        assert n_checked > 500
