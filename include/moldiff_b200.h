@@ -267,6 +267,16 @@ int mdb_radius_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, c
 int mdb_knn_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, const int32_t* seg_hi, int32_t k, int32_t loop,
                   int32_t* counts, int32_t* neighbors, void* stream);
 
+/*
+ * Range check of the tensor-core operands.  The split-fp16 operand planes saturate at +-65504 (cvt.satfinite); every GEMM input
+ * is a LayerNorm / ReLU / sigmoid-bounded activation EXCEPT the two residual streams and what is derived from them linearly.
+ * After a forward on `workspace` (with_backward = 0 layout) this returns max |v| of h_node, h_edge, e = edge_embs(.) and the
+ * node_net table of the LAST block in amax4[0..3] (device floats; NaN / Inf report as Inf), so that a caller can refuse to
+ * trust a checkpoint whose activations leave the fp16 range instead of saturating silently (moldiff_b200/engine.py:
+ * check_operand_range, called by MolDiff.sample on the first step).
+ */
+int mdb_operand_amax(int64_t n_nodes, int64_t n_edges, const float* workspace, float* amax4, void* stream);
+
 /* Profiling: between begin and end every kernel launch of this library is bracketed by CUDA events on
  * its own stream; end synchronises those events and returns summed milliseconds / launch counts per
  * kernel class (arrays of MDB_NUM_KERNEL_CLASSES).  Not for use inside a timed region. */

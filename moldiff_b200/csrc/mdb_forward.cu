@@ -1045,6 +1045,18 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
 #include "mdb_graph_build.cuh"
 #include "mdb_decode.cuh"
 
+// max |v| over a buffer -> atomicMax on the bit pattern (non-negative floats order like unsigned ints); NaN / Inf map to Inf
+__global__ void amax_kernel(const float* __restrict__ v, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = fabsf(v[i]);
+    m = (x > m || x != x) ? (x != x ? INFINITY : x) : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
 }  // namespace
 
 extern "C" {
@@ -1131,6 +1143,23 @@ int mdb_radius_graph(int32_t n_nodes, const float* pos, const int32_t* seg_lo, c
   LAUNCH(MDB_K_graph_build, st,
          (radius_graph_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(n_nodes, pos, seg_lo, seg_hi, radius * radius, loop,
                                                                     max_num_neighbors, counts, neighbors)));
+  return MDB_OK;
+}
+
+int mdb_operand_amax(int64_t n_nodes, int64_t n_edges, const float* workspace, float* amax4, void* stream) {
+  if (!workspace || !amax4 || n_nodes <= 0 || n_edges < 0) return fail(MDB_EINVAL, "mdb_operand_amax: bad arguments%s");
+  Tables tb;
+  carve(tb, const_cast<float*>(workspace), n_nodes, n_edges);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(amax4, 0, 4 * sizeof(float), st));
+  const float* src[4] = {tb.x, tb.hedge, tb.ebuf, tb.hn};
+  const size_t cnt[4] = {(size_t)n_nodes * D, (size_t)n_edges * C, (size_t)n_edges * C, (size_t)n_nodes * D};
+  for (int i = 0; i < 4; ++i) {
+    if (cnt[i] == 0) continue;
+    amax_kernel<<<(int)std::min<size_t>((cnt[i] + 255) / 256, 592), 256, 0, st>>>(src[i], cnt[i], reinterpret_cast<unsigned*>(amax4) + i);
+    ++g_launches;
+  }
+  CUDA_TRY(cudaGetLastError());
   return MDB_OK;
 }
 

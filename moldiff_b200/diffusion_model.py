@@ -326,6 +326,9 @@ class MolDiff(nn.Module, _PackedMixin):
                 preds = graphed.run(step)
             else:
                 preds = self.sample_step(st, step, bond_predictor=bond_predictor, guidance=guidance)
+            if i == 0 and device.type == "cuda" and self._packed_net(device).tc_blob is not None:
+                # first step: the denoiser's unbounded activations must sit inside the fp16 operand range (raises otherwise)
+                engine.check_operand_range(engine.plan_for(st["edge_index"], n_nodes), self.denoiser.num_blocks)
             node_traj[i + 1], pos_traj[i + 1], half_traj[i + 1] = st["h_node"], st["pos"], st["h_half"]
         return {"pred": [preds["pred_node"], preds["pred_pos"], preds["pred_halfedge"]],
                 "traj": [node_traj, pos_traj, half_traj]}

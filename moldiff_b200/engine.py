@@ -101,6 +101,8 @@ def load_library():
         lib.mdb_radius_graph.argtypes = [i32, vp, vp, vp, f32, i32, i32, vp, vp, vp]
         lib.mdb_knn_graph.restype = C.c_int
         lib.mdb_knn_graph.argtypes = [i32, vp, vp, vp, i32, i32, vp, vp, vp]
+        lib.mdb_operand_amax.restype = C.c_int
+        lib.mdb_operand_amax.argtypes = [i64, i64, vp, vp, vp]
         lib.mdb_transition_step.restype = C.c_int
         lib.mdb_transition_step.argtypes = [i32, i32, i32, i32] + [vp] * 26
         lib.mdb_profile_begin.restype = None
@@ -312,6 +314,26 @@ def plan_for(edge_index, n_nodes):
     while len(_plan_cache) > PLAN_CACHE_SIZE:
         _plan_cache.popitem(last=False)
     return plan
+
+
+FP16_OPERAND_LIMIT = 65504.0 / 2       # operand planes saturate at 65504; refuse well before that
+
+
+def check_operand_range(plan: GraphPlan, num_blocks):
+    """After a forward on `plan`: max |v| of the residual streams / e / node_net table that feed the split-fp16 operand planes.
+    Raises if any of them is not finite or within a factor 2 of the fp16 range (where the planes would saturate silently);
+    returns the four values.  One small launch + a 16-byte D2H: MolDiff.sample calls it on its first step only."""
+    lib = load_library()
+    ws = plan.workspace(0, num_blocks)
+    out = torch.zeros(4, dtype=torch.float32, device=plan.device)
+    rc = lib.mdb_operand_amax(plan.n_nodes, plan.n_edges, ws.data_ptr(), out.data_ptr(), _stream_ptr(plan.device))
+    _check(rc, "mdb_operand_amax")
+    vals = dict(zip(("h_node", "h_edge", "e", "node_net"), (float(v) for v in out.cpu())))
+    bad = {k: v for k, v in vals.items() if not (v < FP16_OPERAND_LIMIT)}
+    if bad:
+        raise MoldiffB200Error(f"activations outside the fp16 operand range of the tensor-core path: {bad} "
+                               "(set MDB_DISABLE_TC=1 for the fp32 FFMA kernels)")
+    return vals
 
 
 def net_forward(net: PackedNet, plan: GraphPlan, h_node, pos, h_edge, node_time, edge_time):
