@@ -679,6 +679,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_edge_d.cuh"
 #include "tc_nodeblock16.cuh"
 #include "tc_nodeblock_bwd16.cuh"
+#include "tc_bondffn2.cuh"
 #include "tc_node.cuh"
 #include "tc_edge_tail_bwd.cuh"
 
@@ -818,6 +819,10 @@ int ensure_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN2));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN2));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_fwd2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_d_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_D));
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_fwd16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB16));
@@ -969,10 +974,16 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
       fa.pos = pos_cur; fa.rbf_lo = net->rbf_start; fa.rbf_hi = net->rbf_stop; fa.ebuf = ea.ebuf; fa.sl = ea.sl;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
       fa.dbg = g_dbg_sel == 2 ? g_dbg_stamps : nullptr;
-      if (xf) LAUNCH(MDB_K_tc_bondffn, st,
-                     (tc_bondffn_fwd_kernel<true><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
-      else LAUNCH(MDB_K_tc_bondffn, st,
-                  (tc_bondffn_fwd_kernel<false><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
+      // default: the two-CTAs-per-SM kernel (tc_bondffn2.cuh); MDB_TC_FFN2=0 -> the one-tile-per-SM kernel (A/B runs)
+      static const bool ffn2 = []() { const char* e = getenv("MDB_TC_FFN2"); return e == nullptr || e[0] != '0'; }();
+      const int ffn_grid = (E + tc::ROWS - 1) / tc::ROWS;
+      if (ffn2) {
+        if (xf) LAUNCH(MDB_K_tc_bondffn, st, (tc_bondffn_fwd2_kernel<true><<<ffn_grid, TC_NB_THREADS, SMEM_TC_FFN2, st>>>(fa)));
+        else LAUNCH(MDB_K_tc_bondffn, st, (tc_bondffn_fwd2_kernel<false><<<ffn_grid, TC_NB_THREADS, SMEM_TC_FFN2, st>>>(fa)));
+      } else {
+        if (xf) LAUNCH(MDB_K_tc_bondffn, st, (tc_bondffn_fwd_kernel<true><<<ffn_grid, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
+        else LAUNCH(MDB_K_tc_bondffn, st, (tc_bondffn_fwd_kernel<false><<<ffn_grid, TC_NB_THREADS, SMEM_TC_FFN, st>>>(fa)));
+      }
     } else if (E > 0) {
       LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
     }

@@ -28,12 +28,27 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+// Bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU.  try_wait carries a suspend-time hint: the
+// hardware parks the waiting warp (up to the hint, waking when the phase completes) instead of returning after ~40 cycles,
+// so that a waiting warp does not burn issue slots of its scheduler -- with two CTAs per SM, or next to the service warps,
+// the plain form spent a third of all issued instructions on these loops (ncu source view of tc_bondffn_fwd2_kernel).
+#ifndef MDB_MBAR_HINT_NS
+#define MDB_MBAR_HINT_NS 0   // measured on B200: 2000 ns changes nothing (26.92 vs 26.80 ms per guided step) -- the plain form stays
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 28); ++it) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+#if MDB_MBAR_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"((uint32_t)MDB_MBAR_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -41,6 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
     if (done) return;
   }
   __trap();
