@@ -716,6 +716,7 @@ int ensure_bwd_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD16));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_TAIL_BWD));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_BWD_NODE));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return MDB_OK;
 }
@@ -778,6 +779,11 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
 
   static const bool bwd16_env = []() { const char* e = getenv("MDB_TC_NB_BWD16"); return e == nullptr || e[0] != '0'; }();
   auto nb_tc = [&](int blk) { return net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[blk][MDB_T_BT_NB_G2] >= 0; };
+  // per-node part on tensor cores when every block carries the transposed per-node images (MDB_TC_BWD_NODE=0: fp32 FFMA kernel)
+  static const bool tc_bn_env = []() { const char* e = getenv("MDB_TC_BWD_NODE"); return e == nullptr || e[0] != '0'; }();
+  bool tc_bn = tc_bn_env && net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_head_off[MDB_TH_BT_EDEC1N] >= 0;
+  for (int b = 0; b < L && tc_bn; ++b)
+    tc_bn = net->tc_block_off[b][MDB_T_BT_NB_CEN] >= 0 && net->tc_block_off[b][MDB_T_BT_EB_NFL] >= 0 && net->tc_block_off[b][MDB_T_NB_NN1] >= 0;
   for (int i = L - 1; i >= -1; --i) {
     // node kernel: [final] + phase B(i+1) + phase A(i)
     na.do_final = (i == L - 1);
@@ -795,7 +801,25 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       na.xA = sv.x + (size_t)i * ND; na.aggA = sv.agg + (size_t)i * ND;
       na.tb = tbi;                      // phase A reads block i's saved centroid_lin(x) table
     }
-    LAUNCH(MDB_K_bwd_node, st, (bwd_node_kernel<<<node_tiles, NTHREADS, SMEM_BWD_NODE, st>>>(na)));
+    if (tc_bn) {
+      // tensor-core node kernel (tc_bwd_node.cuh): 128 nodes per CTA, `dx` node-blocked (private to it)
+      TcBwdNodeArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      ba.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob);
+      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) {
+        ba.blkB.o[s] = na.do_B ? net->tc_block_off[i + 1][s] : -1;
+        ba.blkA.o[s] = na.do_A ? net->tc_block_off[i][s] : -1;
+      }
+      for (int s = 0; s < MDB_NUM_TC_HEAD_SLOTS; ++s) ba.hd.o[s] = net->tc_head_off[s];
+      ba.n_nodes = N; ba.do_final = na.do_final; ba.do_B = na.do_B; ba.do_A = na.do_A; ba.red_blocked = na.red_blocked;
+      ba.xB = na.xB; ba.cenA = tbi.cen; ba.aggA = na.aggA; ba.dx = sv.dx; ba.ddect = sv.ddect;
+      ba.dul = sv.dul; ba.dur = sv.dur; ba.dnl = sv.dnl; ba.dgn = sv.dgn; ba.dgx = sv.dgx; ba.dhn = sv.dhn; ba.dagg = sv.dagg;
+      fill_bwd_node_vecs(ba.v, net->blob_host, na.do_B ? &na.blkB : nullptr, na.do_A ? &na.blkA : nullptr);
+      LAUNCH(MDB_K_tc_node_bwd, st,
+             (tc_bwd_node_kernel<<<(N + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_BWD_NODE, st>>>(ba)));
+    } else {
+      LAUNCH(MDB_K_bwd_node, st, (bwd_node_kernel<<<node_tiles, NTHREADS, SMEM_BWD_NODE, st>>>(na)));
+    }
     if (i < 0) break;
     fill_blk(ea.off, net, i);
     ea.tb = tbi;

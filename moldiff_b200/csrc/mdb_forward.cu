@@ -682,6 +682,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_bondffn2.cuh"
 #include "tc_node.cuh"
 #include "tc_edge_tail_bwd.cuh"
+#include "tc_bwd_node.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -756,7 +757,7 @@ struct Saved {
   float *agg;                // [L][N][256]  aggregated NodeBlock messages of block i
   float *slsr;               // [L][2][N][64]
   float *tabs;               // [L][N * TAB_FLOATS]  per-node hoisted tables of every block (hn, gx, cen, nl, gn, fl, fr)
-  float *dx;                 // [N][256]  running d/d h_node
+  float *dx;                 // [pad64(N)][256]  running d/d h_node (row-major: bwd_node_kernel; node-blocked: tc_bwd_node_kernel)
   float *dh, *de;            // [E][64]   d/d h_edge (block output -> block input), d/d e
   float *dg;                 // [E][16]   d/d rbf features, summed over blocks
   float *dul, *dur;          // [N][64]   sum_{p: l_p = n} du_p, sum_{p: r_p = n} du_p
@@ -788,7 +789,7 @@ size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   auto take = [&](size_t n) { float* p = base ? base + o : nullptr; o += al(n); return p; };
   sv.e = take(L * E * C); sv.x = take(L * N * D); sv.agg = take(L * N * D); sv.slsr = take(L * 2 * N * C);
   sv.tabs = take(L * N * TAB_FLOATS);
-  sv.dx = take(N * D); sv.dh = take(E * C); sv.de = take(E * C); sv.dg = take(E * G);
+  sv.dx = take(pad64(N) * D); sv.dh = take(E * C); sv.de = take(E * C); sv.dg = take(E * G);
   sv.dul = take(N * C); sv.dur = take(N * C);
   sv.dagg = take(N * D); sv.dgx = take(pad64(N) * D); sv.dhn = take(pad64(N) * D);   // dgx / dhn: row-major or node-blocked
   sv.hnb = take(L * pad64(N) * D); sv.gxb = take(L * pad64(N) * D);
