@@ -716,6 +716,7 @@ int ensure_bwd_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_nodeblock_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_NB_BWD16));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_TAIL_BWD));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD2));
   CUDA_TRY(cudaFuncSetAttribute(tc_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_BWD_NODE));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return MDB_OK;
@@ -872,8 +873,13 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       fa.e = ea.e; fa.dul = sv.dul; fa.dur = sv.dur; fa.dnl = sv.dnl; fa.dgn = sv.dgn;
       fa.de_in = sv.de; fa.dh = sv.dh; fa.dg = sv.dg;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
-      LAUNCH(MDB_K_tc_bondffn_bwd, st,
-             (tc_bondffn_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN_BWD, st>>>(fa)));
+      static const bool ffn_bwd2 = []() { const char* e = getenv("MDB_TC_FFN_BWD2"); return e == nullptr || e[0] != '0'; }();
+      if (ffn_bwd2)
+        LAUNCH(MDB_K_tc_bondffn_bwd, st,
+               (tc_bondffn_bwd2_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN_BWD2, st>>>(fa)));
+      else
+        LAUNCH(MDB_K_tc_bondffn_bwd, st,
+               (tc_bondffn_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN_BWD, st>>>(fa)));
     } else {
       LAUNCH(MDB_K_bwd_edge_bondffn, st, (bwd_edge_bondffn_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_FFN, st>>>(ea)));
     }

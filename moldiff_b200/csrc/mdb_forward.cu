@@ -682,6 +682,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_bondffn2.cuh"
 #include "tc_node.cuh"
 #include "tc_edge_tail_bwd.cuh"
+#include "tc_bondffn_bwd2.cuh"
 #include "tc_bwd_node.cuh"
 
 // ------------------------------------------------------------------------------------------------

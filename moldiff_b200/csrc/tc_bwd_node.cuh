@@ -9,9 +9,11 @@
 //   first launch of a backward: dx = ddect W_dec1n                                      (bond_predictor.py:155-160)
 //
 // 128 nodes per CTA, two threads per row (128 columns each), rolled 16-column epilogues.  Everything that is linear in the
-// incoming gradients accumulates in ONE TMEM accumulator D0 (fourteen K stages of different operands chained with
-// accumulate = 1); the running gradient itself is added on the CUDA cores when D0 is read (dx_new = dx_in + D0), so it never
-// needs operand planes of its own.  D1 is the scratch accumulator of the two LayerNorm backwards; the normalised activations
+// incoming gradients accumulates in ONE chain (fourteen K stages of different operands, accumulate = 1): main terms
+// (hi * hi) in D0, cross terms in D1 whenever D1 is free (tc_pipe.cuh: gemm_split -- the hardware's truncating accumulate
+// would otherwise shrink the running gradient coherently, 1.7e-5 on the guidance gradient instead of 6e-6); the running
+// gradient itself is added on the CUDA cores when the chain is read (dx_new = dx_in + D0 + D1), so it never needs operand
+// planes of its own.  D1 is also the scratch accumulator of the two LayerNorm backwards; the normalised activations
 // of the node tail are parked, as fp16 hi|lo planes, in the very shared-memory bytes that the dc operand planes overwrite.
 // The running gradient `dx` lives in the node-blocked layout (tile_engine.cuh: blk_off) -- it is private to this kernel --
 // so a warp's row threads read and write it as 512 contiguous bytes per instruction.
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * tc::ROWS;
-  tc::Pipe p;
+  tc::PipeT<tc::NSTAGE, true> p;       // cross-first order for the stand-alone GEMMs; the chain uses gemm_split
   tc::pipe_init<TC_NRW>(p, ps, stages);
   if (warp == TC_NRW) tc::tmem_alloc<512>(&ps->tmem_base);
   {
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       tc::rows_publish(p);
     }
     // ---- the chain into D0: d a1 W1, then the gradients of every hoisted per-node projection -------------------------
-    tc::gemm<D, D>(p, p_hi, p_lo, TCBB_(BT_NB_NN1), D0, false, true, true);
+    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBB_(BT_NB_NN1), D0, D1, false, false, true, true);   // (a1 in D1 is dead)
     uint8_t* q0_hi = P;                              // [dul (K = 64) | dur (K = 64) | dnl_L (K = 128)]
     uint8_t* q0_lo = q0_hi + tc::ROWS * C * 2;
     uint8_t* q1_hi = q0_lo + tc::ROWS * C * 2;
@@ -232,9 +234,9 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       stage_cols<128, 64>(q2_hi, q2_lo, row, half * 64, valid ? a.dnl + nn * 128 + half * 64 : nullptr);
       tc::rows_publish(p);
     }
-    tc::gemm<C, D>(p, q0_hi, q0_lo, TCBB_(BT_EB_NFL), D0, true, true, false);
-    tc::gemm<C, D>(p, q1_hi, q1_lo, TCBB_(BT_EB_NFR), D0, true, false, false);
-    tc::gemm<128, D>(p, q2_hi, q2_lo, TCBB_(BT_EL_NL), D0, true, false, true);
+    tc::gemm_split<C, D>(p, q0_hi, q0_lo, TCBB_(BT_EB_NFL), D0, D1, true, true, true, false);
+    tc::gemm_split<C, D>(p, q1_hi, q1_lo, TCBB_(BT_EB_NFR), D0, D1, true, true, false, false);
+    tc::gemm_split<128, D>(p, q2_hi, q2_lo, TCBB_(BT_EL_NL), D0, D1, true, true, false, true);
     uint8_t* r0_hi = P;                              // [dnl_R (K = 128) | dgn_L (K = 32) | dgn_R (K = 32)]
     uint8_t* r0_lo = r0_hi + tc::ROWS * 128 * 2;
     uint8_t* r1_hi = r0_lo + tc::ROWS * 128 * 2;
@@ -248,9 +250,9 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       stage_cols<32, 16>(r2_hi, r2_lo, row, half * 16, valid ? a.dgn + (size_t)a.n_nodes * 32 + nn * 32 + half * 16 : nullptr);
       tc::rows_publish(p);
     }
-    tc::gemm<128, D>(p, r0_hi, r0_lo, TCBB_(BT_ER_NL), D0, true, true, false);
-    tc::gemm<32, D>(p, r1_hi, r1_lo, TCBB_(BT_EL_GN), D0, true, false, false);
-    tc::gemm<32, D>(p, r2_hi, r2_lo, TCBB_(BT_ER_GN), D0, true, false, true);
+    tc::gemm_split<128, D>(p, r0_hi, r0_lo, TCBB_(BT_ER_NL), D0, D1, true, true, true, false);
+    tc::gemm_split<32, D>(p, r1_hi, r1_lo, TCBB_(BT_EL_GN), D0, D1, true, true, false, false);
+    tc::gemm_split<32, D>(p, r2_hi, r2_lo, TCBB_(BT_ER_GN), D0, D1, true, true, false, true);
     if (p.role == 0) {
       tc::rows_wait_acc(p);
 #pragma unroll 1
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       }
       tc::rows_publish(p);
     }
-    tc::gemm<D, D>(p, p_hi, p_lo, TCBB_(BT_NB_GX), D0, true, true, true);
+    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBB_(BT_NB_GX), D0, D1, true, true, true, true);
   } else {
     // first launch of a backward: dx = ddect W_dec1n  (nothing has reached the node path yet)
     uint8_t* s_hi = P;
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       stage_cols<C, 32>(s_hi, s_lo, row, half * 32, (valid && a.do_final) ? a.ddect + nn * C + half * 32 : nullptr);
       tc::rows_publish(p);
     }
-    tc::gemm<C, D>(p, s_hi, s_lo, a.tc_blob + a.hd.o[MDB_TH_BT_EDEC1N], D0, false, true, true);
+    tc::gemm_split<C, D>(p, s_hi, s_lo, a.tc_blob + a.hd.o[MDB_TH_BT_EDEC1N], D0, D1, false, false, true, true);
   }
 
   if (a.do_A) {
@@ -288,14 +290,17 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
     if (p.role == 0) {
       tc::rows_wait_acc(p);                          // D0 = everything linear so far ; the planes are free
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {                  // dx_new = dx_in + D0 -> planes
-        float v[16], d[16];
+      for (int c = 0; c < 8; ++c) {                  // dx_new = dx_in + (D0 + D1) -> planes ; D0 <- D0 + D1 (D1 is reused below)
+        float v[16], d[16], x[16];
         tc::tmem_ld16(T0 + c * 16, d);
+        tc::tmem_ld16(T1 + c * 16, x);
         ld_blocked16(a.dx, n, hc + c * 16, valid && have_dx_in, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += d[i];
+        for (int i = 0; i < 16; ++i) { d[i] += x[i]; v[i] += d[i]; }
+        tc::tmem_st16(T0 + c * 16, d);
         store_a16(p_hi, p_lo, row, hc + c * 16, v);
       }
+      tc::tmem_st_wait();
       tc::rows_publish(p);
       // statistics of u = cen + agg while the GEMM below runs
       RunStat rs = {0.f, 0.f, 0.f};
@@ -367,18 +372,19 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       }
       tc::rows_publish(p);
     }
-    tc::gemm<D, D>(p, p_hi, p_lo, TCBA_(BT_NB_CEN), D0, true, true, true);            // + dc W_cen
+    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBA_(BT_NB_CEN), D0, D1, true, false, true, true);   // + dc W_cen (d xhat in D1 is dead)
   }
 
   if (p.role == 0) {
     tc::rows_wait_acc(p);
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {                    // dx_out = dx_in + D0
-      float v[16], d[16];
+    for (int c = 0; c < 8; ++c) {                    // dx_out = dx_in + D0 (main terms) + D1 (cross terms)
+      float v[16], d[16], x[16];
       tc::tmem_ld16(T0 + c * 16, d);
+      tc::tmem_ld16(T1 + c * 16, x);
       ld_blocked16(a.dx, n, hc + c * 16, valid && have_dx_in, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += d[i];
+      for (int i = 0; i < 16; ++i) v[i] += d[i] + x[i];
       if (valid) st_blocked16(a.dx, n, hc + c * 16, v);
     }
     if (a.do_A) {

@@ -246,4 +246,53 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT, XF>& p, const uint8_t* a_hi, c
   }
 }
 
+// Same pipeline, main and cross terms in DIFFERENT accumulators:  D[d_col] (+)= A_hi W_hi ;  D[d_col_x] (+)= A_lo W_hi + A_hi W_lo.
+// For long accumulation CHAINS (tc_bwd_node.cuh: fourteen K stages of seven different operands into one accumulator): a cross
+// term added to an accumulator that already holds the 2^11 x larger main terms costs ~1/2 ulp of the LARGE value, towards
+// zero, per instruction (see the accumulation-order note above) -- two thirds of the instructions of a chain.  Kept apart,
+// the cross terms truncate at their own 2^-11 scale and the caller adds the two tiles on the CUDA cores (round-to-nearest).
+// Interleaved K order (every weight stage is streamed once), whatever the pipe's XF flag says.
+template <int K, int N, int NSLOT, bool XF>
+__device__ __forceinline__ void gemm_split(PipeT<NSLOT, XF>& p, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_img,
+                                           uint32_t d_col, uint32_t d_col_x, bool accumulate, bool accumulate_x, bool wait_ready,
+                                           bool signal_done) {
+  using WS = WStage<N, KB>;
+  constexpr int NS = K / KB;
+  static_assert(K % KB == 0, "K must be a multiple of the stage depth");
+  if (p.role == 1) {
+    for (int s = 0; s < NS; ++s, ++p.it) {
+      const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
+      mbar_wait(&p.s->empty[slot], ph ^ 1);
+      stage_load_elect(p.stages + slot * p.slot_bytes, w_img + (size_t)s * WS::STAGE_BYTES, WS::STAGE_BYTES, &p.s->full[slot]);
+    }
+  } else if (p.role == 2) {
+    if (wait_ready) {
+      const uint32_t ready_parity = p.n_ready & 1;
+      ++p.n_ready;
+      mbar_wait(&p.s->a_ready[NGRP - 1], ready_parity);
+      fence_after_sync();
+    }
+    constexpr uint32_t idesc = make_idesc_f16(ROWS, N, OPERAND_FMT, OPERAND_FMT);
+    constexpr uint32_t SBO_A = (K / 8) * 128;
+    const uint32_t d_main = p.s->tmem_base + d_col, d_x = p.s->tmem_base + d_col_x;
+    const uint64_t da_hi0 = make_smem_desc(smem_u32(a_hi), 128, SBO_A);
+    const uint64_t da_lo0 = make_smem_desc(smem_u32(a_lo), 128, SBO_A);
+    const uint64_t db0 = make_smem_desc(smem_u32(p.stages), 128, WS::SBO);
+    const uint32_t slot_units = p.slot_bytes >> 4;
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s, ++p.it) {
+      const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
+      mbar_wait(&p.s->full[slot], ph);
+      fence_after_sync();
+      const uint64_t da_hi = da_hi0 + (uint32_t)s * 16u, da_lo = da_lo0 + (uint32_t)s * 16u;
+      const uint64_t db_hi = db0 + slot * slot_units, db_lo = db_hi + (WS::PLANE_BYTES >> 4);
+      mma_f16_ss_elect<false>(d_main, da_hi, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
+      mma_f16_ss_elect<false>(d_x, da_lo, db_hi, idesc, (accumulate_x || s > 0) ? 1u : 0u);
+      mma_f16_ss_elect<true>(d_x, da_hi, db_lo, idesc);
+      mma_commit_elect(&p.s->empty[slot]);
+    }
+    if (signal_done) mma_commit_elect(&p.s->done);
+  }
+}
+
 }  // namespace tc
