@@ -46,7 +46,9 @@ def parse():
                                                             "1024 for train_fwd, 32 for --simple)")
     ap.add_argument("--simple", action="store_true",
                     help="BASELINE config 1: sample_MolDiff_simple.yml (train_MolDiff_simple.yml weights), T = 50, B = 32, unguided")
-    ap.add_argument("--graph", action="store_true", help="replay the sampler loop body as one CUDA graph (MolDiff.graphed_step)")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="replay the sampler loop body as one CUDA graph (MolDiff.graphed_step) -- the default, as in MolDiff.sample")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches (one per kernel)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: --batch is the GLOBAL batch, split over the ranks by balancing sum n^2 (FLOPs)")
     ap.add_argument("--max-size", type=int, default=None,

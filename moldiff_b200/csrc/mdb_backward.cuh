@@ -749,8 +749,8 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
   // Scatter accumulators of block L-1 (every later block's are re-zeroed by bwd_node_kernel after it consumed them).  They
   // are left zero by a completed backward, but a FRESH workspace (torch.empty, recycled allocator blocks) is not: zero them
   // here instead of relying on it.
-  CUDA_TRY(cudaMemsetAsync(sv.dul, 0, NC * sizeof(float), st));
-  CUDA_TRY(cudaMemsetAsync(sv.dur, 0, NC * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dul, 0, 2 * NC * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(sv.dur, 0, 2 * NC * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(sv.dgx, 0, (size_t)pad64(N) * D * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(sv.dhn, 0, (size_t)pad64(N) * D * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(sv.dnl, 0, (size_t)2 * N * 128 * sizeof(float), st));
@@ -778,6 +778,9 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
   ea.blob = net->blob; ea.tb = tb; ea.sv = sv; ea.left = plan->left; ea.right = plan->right;
   ea.n_nodes = N; ea.n_edges = E;
 
+  static const bool overlap_env = []() { const char* e = getenv("MDB_OVERLAP"); return e == nullptr || e[0] != '0'; }();
+  const bool overlap = overlap_env && !g_profiling;
+  SideStream* side = overlap ? side_stream() : nullptr;
   static const bool bwd16_env = []() { const char* e = getenv("MDB_TC_NB_BWD16"); return e == nullptr || e[0] != '0'; }();
   auto nb_tc = [&](int blk) { return net->tc_blob != nullptr && net->blob_host != nullptr && net->tc_block_off[blk][MDB_T_BT_NB_G2] >= 0; };
   // per-node part on tensor cores when every block carries the transposed per-node images (MDB_TC_BWD_NODE=0: fp32 FFMA kernel)
@@ -802,6 +805,21 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       na.xA = sv.x + (size_t)i * ND; na.aggA = sv.agg + (size_t)i * ND;
       na.tb = tbi;                      // phase A reads block i's saved centroid_lin(x) table
     }
+    // dul / dur are parity-buffered by block: this launch reads block i + 1's sums and re-zeroes that buffer (block i - 1 will
+    // accumulate into it); block i's tail kernel accumulates into the other one -- so the node kernel and the tail kernel of
+    // block i are independent and run side by side: the node kernel (50 long CTAs) on the high-priority side stream.
+    float* dul_rd = sv.dul + (size_t)((i + 1) & 1) * NC;
+    float* dur_rd = sv.dur + (size_t)((i + 1) & 1) * NC;
+    float* dul_cur = sv.dul + (size_t)(i & 1) * NC;
+    float* dur_cur = sv.dur + (size_t)(i & 1) * NC;
+    na.sv.dul = dul_rd; na.sv.dur = dur_rd;
+    ea.sv.dul = dul_cur; ea.sv.dur = dur_cur;
+    const bool forked = overlap && side != nullptr && i >= 0;
+    cudaStream_t nst = forked ? side->s : st;
+    if (forked) {
+      CUDA_TRY(cudaEventRecord(side->fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
+    }
     if (tc_bn) {
       // tensor-core node kernel (tc_bwd_node.cuh): 128 nodes per CTA, `dx` node-blocked (private to it)
       TcBwdNodeArgs ba;
@@ -814,13 +832,14 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       for (int s = 0; s < MDB_NUM_TC_HEAD_SLOTS; ++s) ba.hd.o[s] = net->tc_head_off[s];
       ba.n_nodes = N; ba.do_final = na.do_final; ba.do_B = na.do_B; ba.do_A = na.do_A; ba.red_blocked = na.red_blocked;
       ba.xB = na.xB; ba.cenA = tbi.cen; ba.aggA = na.aggA; ba.dx = sv.dx; ba.ddect = sv.ddect;
-      ba.dul = sv.dul; ba.dur = sv.dur; ba.dnl = sv.dnl; ba.dgn = sv.dgn; ba.dgx = sv.dgx; ba.dhn = sv.dhn; ba.dagg = sv.dagg;
+      ba.dul = dul_rd; ba.dur = dur_rd; ba.dnl = sv.dnl; ba.dgn = sv.dgn; ba.dgx = sv.dgx; ba.dhn = sv.dhn; ba.dagg = sv.dagg;
       fill_bwd_node_vecs(ba.v, net->blob_host, na.do_B ? &na.blkB : nullptr, na.do_A ? &na.blkA : nullptr);
-      LAUNCH(MDB_K_tc_node_bwd, st,
-             (tc_bwd_node_kernel<<<(N + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_BWD_NODE, st>>>(ba)));
+      LAUNCH(MDB_K_tc_node_bwd, nst,
+             (tc_bwd_node_kernel<<<(N + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_BWD_NODE, nst>>>(ba)));
     } else {
-      LAUNCH(MDB_K_bwd_node, st, (bwd_node_kernel<<<node_tiles, NTHREADS, SMEM_BWD_NODE, st>>>(na)));
+      LAUNCH(MDB_K_bwd_node, nst, (bwd_node_kernel<<<node_tiles, NTHREADS, SMEM_BWD_NODE, nst>>>(na)));
     }
+    if (forked) CUDA_TRY(cudaEventRecord(side->join, side->s));
     if (i < 0) break;
     fill_blk(ea.off, net, i);
     ea.tb = tbi;
@@ -832,13 +851,14 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       ta.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob);
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) ta.tco.o[s] = net->tc_block_off[i][s];
       ta.left = plan->left; ta.right = plan->right; ta.n_nodes = N; ta.n_edges = E;
-      ta.e = ea.e; ta.dh = sv.dh; ta.sl = ea.sl; ta.fl = ea.fl; ta.fr = ea.fr; ta.dul = sv.dul; ta.dur = sv.dur; ta.de = sv.de;
+      ta.e = ea.e; ta.dh = sv.dh; ta.sl = ea.sl; ta.fl = ea.fl; ta.fr = ea.fr; ta.dul = dul_cur; ta.dur = dur_cur; ta.de = sv.de;
       fill_edge_tail_bwd_vecs(ta.v, net->blob_host, ea.off);
       LAUNCH(MDB_K_tc_edge_tail_bwd, st,
              (tc_edge_tail_bwd_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_TAIL_BWD, st>>>(ta)));
     } else {
       LAUNCH(MDB_K_bwd_edge_tail, st, (bwd_edge_tail_kernel<<<edge_tiles, NTHREADS, SMEM_BWD_TAIL, st>>>(ea)));
     }
+    if (forked) CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));     // the NodeBlock backward needs dagg (node kernel) and de (tail)
     if (nb_tc(i)) {
       if (bwd16_env) {
         TcNbBwd16Args ta;
@@ -870,7 +890,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       fa.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); fa.tb = tbi;
       for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) fa.tco.o[s] = net->tc_block_off[i][s];
       fa.left = plan->left; fa.right = plan->right; fa.n_nodes = N; fa.n_edges = E;
-      fa.e = ea.e; fa.dul = sv.dul; fa.dur = sv.dur; fa.dnl = sv.dnl; fa.dgn = sv.dgn;
+      fa.e = ea.e; fa.dul = dul_cur; fa.dur = dur_cur; fa.dnl = sv.dnl; fa.dgn = sv.dgn;
       fa.de_in = sv.de; fa.dh = sv.dh; fa.dg = sv.dg;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
       static const bool ffn_bwd2 = []() { const char* e = getenv("MDB_TC_FFN_BWD2"); return e == nullptr || e[0] != '0'; }();

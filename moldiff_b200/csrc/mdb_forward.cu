@@ -731,6 +731,24 @@ inline int persistent_grid(int64_t n_tiles) {
   }();
   return (int)(n_tiles < sms ? (n_tiles > 0 ? n_tiles : 1) : sms);
 }
+// A second, HIGH-PRIORITY stream (per device) for the few-CTA node kernels that may run next to an edge kernel of the main
+// chain (their CTAs are then placed first as SMs free up), and the two events that fork / join it.
+// Fork / join by events keeps the pair capturable into one CUDA graph (MolDiff.graphed_step).
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideStream* side_stream() {
+  static SideStream ss[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& x = ss[dev];
+  if (!x.s) {
+    int lo = 0, hi = 0;                      // (numerically lower = higher priority)
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&x.s, cudaStreamNonBlocking, hi) != cudaSuccess) { x.s = nullptr; return nullptr; }
+    cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming);
+  }
+  return &x;
+}
 inline int64_t pad64(int64_t n) { return (n + 63) / 64 * 64; }   // node-blocked tables (tile_engine.cuh: blk_off)
 
 size_t carve(Tables& tb, float* base, int64_t N, int64_t E) {
@@ -761,7 +779,7 @@ struct Saved {
   float *dx;                 // [pad64(N)][256]  running d/d h_node (row-major: bwd_node_kernel; node-blocked: tc_bwd_node_kernel)
   float *dh, *de;            // [E][64]   d/d h_edge (block output -> block input), d/d e
   float *dg;                 // [E][16]   d/d rbf features, summed over blocks
-  float *dul, *dur;          // [N][64]   sum_{p: l_p = n} du_p, sum_{p: r_p = n} du_p
+  float *dul, *dur;          // [2][N][64]   sum_{p: l_p = n} du_p, sum_{p: r_p = n} du_p; parity = block index & 1
   float *dagg, *dgx, *dhn;   // [N][256]
   float *dnl;                // [2][N][128]
   float *dgn;                // [2][N][32]
@@ -791,7 +809,7 @@ size_t carve_saved(Saved& sv, float* base, int64_t N, int64_t E, int64_t L) {
   sv.e = take(L * E * C); sv.x = take(L * N * D); sv.agg = take(L * N * D); sv.slsr = take(L * 2 * N * C);
   sv.tabs = take(L * N * TAB_FLOATS);
   sv.dx = take(pad64(N) * D); sv.dh = take(E * C); sv.de = take(E * C); sv.dg = take(E * G);
-  sv.dul = take(N * C); sv.dur = take(N * C);
+  sv.dul = take(2 * N * C); sv.dur = take(2 * N * C);   // two parity buffers each (block i / block i + 1)
   sv.dagg = take(N * D); sv.dgx = take(pad64(N) * D); sv.dhn = take(pad64(N) * D);   // dgx / dhn: row-major or node-blocked
   sv.hnb = take(L * pad64(N) * D); sv.gxb = take(L * pad64(N) * D);
   sv.dnl = take(2 * N * 128); sv.dgn = take(2 * N * 32); sv.ddect = take(N * C);
@@ -924,6 +942,11 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
   const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
   const bool xf = cross_first(net);
+  // side-stream overlap of the EdgeBlock tail (see the block loop): networks without a position update, not while the
+  // per-kernel event profile is being taken (mdb_profile_begin), MDB_OVERLAP=0 disables it
+  static const bool overlap_env = []() { const char* e = getenv("MDB_OVERLAP"); return e == nullptr || e[0] != '0'; }();
+  const bool overlap = overlap_env && !g_profiling && !net->update_pos;
+  SideStream* side = overlap ? side_stream() : nullptr;
 
   LAUNCH(MDB_K_node_init, st,
          (node_init_kernel<<<N, D, 0, st>>>(net->kind, N, net->num_node_types, net->time_dim, net->num_timesteps,
@@ -989,6 +1012,28 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     } else if (E > 0) {
       LAUNCH(MDB_K_edge_b, st, (edge_kernel_b<<<edge_tiles, NTHREADS, SMEM_EDGE_B, st>>>(ea)));
     }
+    // EdgeBlock tail (+ PosUpdate) of block i.  Without a position update (bond predictor) it depends on the BondFFN kernel
+    // above only -- not on the NodeBlock / node kernels below (h_edge' = f(e, SL, SR, fl, fr); the tables of block i + 1 go
+    // to the other parity buffers) -- so the two run side by side: the node kernel (50 ... 99 long-running CTAs) on the
+    // high-priority side stream, this kernel's 1 228 short CTAs on the SMs it leaves free.
+    auto launch_edge_d = [&](cudaStream_t s_) {
+      if (E > 0 && tc_nb && net->tc_block_off[i][MDB_T_EB_SELF] >= 0) {
+        TcEdgeDArgs da;
+        memset(&da, 0, sizeof(da));
+        da.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); da.tb = tbi;
+        for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) da.tco.o[s] = net->tc_block_off[i][s];
+        da.left = plan->left; da.right = plan->right; da.n_nodes = N; da.n_edges = E; da.update_pos = net->update_pos;
+        da.ebuf = ea.ebuf; da.sl = ea.sl; da.fl = ea.fl; da.fr = ea.fr; da.pos_cur = pos_cur; da.pos_nxt = pos_nxt;
+        fill_edge_d_vecs(da.v, net->blob_host, ea.off, net->update_pos != 0);
+        if (xf) LAUNCH(MDB_K_tc_edge_d, s_,
+                       (tc_edge_d_kernel<true><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, s_>>>(da)));
+        else LAUNCH(MDB_K_tc_edge_d, s_,
+                    (tc_edge_d_kernel<false><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, s_>>>(da)));
+      } else if (E > 0) {
+        LAUNCH(MDB_K_edge_d, s_, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, s_>>>(ea)));
+      }
+    };
+    const bool forked = overlap && side != nullptr && E > 0 && tc_ffn;
     if (E > 0 && tc_nb) {
       TcNbArgs ta;
       memset(&ta, 0, sizeof(ta));
@@ -1015,22 +1060,16 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     na.x_save = (in.save && i + 1 < L) ? sv.x + (size_t)(i + 1) * ND : nullptr;
     na.agg_save = in.save ? sv.agg + (size_t)i * ND : nullptr;
     na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
-    rc = launch_node(net, na, i, na.do_pre ? i + 1 : -1, node_tiles, st);
+    if (forked) {                                    // node kernel on the high-priority side stream, tail kernel on the main one
+      CUDA_TRY(cudaEventRecord(side->fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
+    }
+    rc = launch_node(net, na, i, na.do_pre ? i + 1 : -1, node_tiles, forked ? side->s : st);
     if (rc) return rc;
-    if (E > 0 && tc_nb && net->tc_block_off[i][MDB_T_EB_SELF] >= 0) {
-      TcEdgeDArgs da;
-      memset(&da, 0, sizeof(da));
-      da.tc_blob = reinterpret_cast<const uint8_t*>(net->tc_blob); da.tb = tbi;
-      for (int s = 0; s < MDB_NUM_TC_SLOTS; ++s) da.tco.o[s] = net->tc_block_off[i][s];
-      da.left = plan->left; da.right = plan->right; da.n_nodes = N; da.n_edges = E; da.update_pos = net->update_pos;
-      da.ebuf = ea.ebuf; da.sl = ea.sl; da.fl = ea.fl; da.fr = ea.fr; da.pos_cur = pos_cur; da.pos_nxt = pos_nxt;
-      fill_edge_d_vecs(da.v, net->blob_host, ea.off, net->update_pos != 0);
-      if (xf) LAUNCH(MDB_K_tc_edge_d, st,
-                     (tc_edge_d_kernel<true><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, st>>>(da)));
-      else LAUNCH(MDB_K_tc_edge_d, st,
-                  (tc_edge_d_kernel<false><<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_EDGE_D, st>>>(da)));
-    } else if (E > 0) {
-      LAUNCH(MDB_K_edge_d, st, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, st>>>(ea)));
+    launch_edge_d(st);
+    if (forked) {                                    // join: the next block needs both
+      CUDA_TRY(cudaEventRecord(side->join, side->s));
+      CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
     }
     if (net->update_pos) { const float* t_ = pos_cur; pos_cur = pos_nxt; pos_nxt = const_cast<float*>(t_); }
   }

@@ -89,6 +89,7 @@ class MolDiff(nn.Module, _PackedMixin):
         self._packed = None
         self._packed_key = None
         self.fused_transition = True     # CUDA tensors: posterior sampling in one launch (False = unfused PyTorch ops)
+        self.cuda_graph = True           # sample(): replay the loop body as one CUDA graph (discrete space + fused transition)
 
     # ---- weights ----
     def _pack(self, device):
@@ -318,7 +319,8 @@ class MolDiff(nn.Module, _PackedMixin):
             steps = tqdm(steps, total=T)
         preds = None
         graphed = None
-        if getattr(self, "cuda_graph", False) and device.type == "cuda":
+        if (getattr(self, "cuda_graph", False) and device.type == "cuda" and self.categorical_space == "discrete"
+                and self.fused_transition):
             graphed = self.graphed_step(st, bond_predictor=bond_predictor, guidance=guidance)
             st = graphed.st
         for i, step in enumerate(steps):
