@@ -942,10 +942,10 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   for (int s = 0; s < MDB_NUM_HEAD_SLOTS; ++s) head.o[s] = (int)net->head_off[s];
   const int node_tiles = (N + TM - 1) / TM, edge_tiles = (E + TM - 1) / TM;
   const bool xf = cross_first(net);
-  // side-stream overlap of the EdgeBlock tail (see the block loop): networks without a position update, not while the
+  // side-stream overlap of the node kernels with the EdgeBlock tail / PosUpdate kernel (see the block loop); not while the
   // per-kernel event profile is being taken (mdb_profile_begin), MDB_OVERLAP=0 disables it
   static const bool overlap_env = []() { const char* e = getenv("MDB_OVERLAP"); return e == nullptr || e[0] != '0'; }();
-  const bool overlap = overlap_env && !g_profiling && !net->update_pos;
+  const bool overlap = overlap_env && !g_profiling;
   SideStream* side = overlap ? side_stream() : nullptr;
 
   LAUNCH(MDB_K_node_init, st,
@@ -1033,7 +1033,8 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
         LAUNCH(MDB_K_edge_d, s_, (edge_kernel_d<<<edge_tiles, NTHREADS, SMEM_EDGE_D, s_>>>(ea)));
       }
     };
-    const bool forked = overlap && side != nullptr && E > 0 && tc_ffn;
+    const bool forked = overlap && side != nullptr && E > 0 && tc_ffn && !net->update_pos;
+    const bool forked_pre = overlap && side != nullptr && E > 0 && tc_ffn && net->update_pos;
     if (E > 0 && tc_nb) {
       TcNbArgs ta;
       memset(&ta, 0, sizeof(ta));
@@ -1063,13 +1064,31 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
     if (forked) {                                    // node kernel on the high-priority side stream, tail kernel on the main one
       CUDA_TRY(cudaEventRecord(side->fork, st));
       CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
-    }
-    rc = launch_node(net, na, i, na.do_pre ? i + 1 : -1, node_tiles, forked ? side->s : st);
-    if (rc) return rc;
-    launch_edge_d(st);
-    if (forked) {                                    // join: the next block needs both
+      rc = launch_node(net, na, i, na.do_pre ? i + 1 : -1, node_tiles, side->s);
+      if (rc) return rc;
+      launch_edge_d(st);
+      CUDA_TRY(cudaEventRecord(side->join, side->s));
+      CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));       // join: the next block needs both
+    } else if (forked_pre && na.do_pre) {
+      // With a position update the tail / PosUpdate kernel needs this block's `mid` half (new h_node -> lf / rf, pos_nxt) but
+      // not the hoisted tables of block i + 1: `mid` stays in the chain, `pre` runs beside the edge kernel.
+      NodeArgs nm = na;
+      nm.do_pre = 0;
+      rc = launch_node(net, nm, i, -1, node_tiles, st);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(side->fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
+      NodeArgs np = na;
+      np.do_mid = 0; np.do_dec = 0;
+      rc = launch_node(net, np, -1, i + 1, node_tiles, side->s);
+      if (rc) return rc;
+      launch_edge_d(st);
       CUDA_TRY(cudaEventRecord(side->join, side->s));
       CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+    } else {
+      rc = launch_node(net, na, i, na.do_pre ? i + 1 : -1, node_tiles, st);
+      if (rc) return rc;
+      launch_edge_d(st);
     }
     if (net->update_pos) { const float* t_ = pos_cur; pos_cur = pos_nxt; pos_nxt = const_cast<float*>(t_); }
   }

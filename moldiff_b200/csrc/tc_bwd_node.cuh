@@ -9,11 +9,13 @@
 //   first launch of a backward: dx = ddect W_dec1n                                      (bond_predictor.py:155-160)
 //
 // 128 nodes per CTA, two threads per row (128 columns each), rolled 16-column epilogues.  Everything that is linear in the
-// incoming gradients accumulates in ONE chain (fourteen K stages of different operands, accumulate = 1): main terms
-// (hi * hi) in D0, cross terms in D1 whenever D1 is free (tc_pipe.cuh: gemm_split -- the hardware's truncating accumulate
-// would otherwise shrink the running gradient coherently, 1.7e-5 on the guidance gradient instead of 6e-6); the running
-// gradient itself is added on the CUDA cores when the chain is read (dx_new = dx_in + D0 + D1), so it never needs operand
-// planes of its own.  D1 is also the scratch accumulator of the two LayerNorm backwards; the normalised activations
+// incoming gradients runs as a chain of five stages (fourteen K stages of seven different operands); within a stage the
+// main terms (hi * hi) accumulate in D0 and the cross terms in D1 (tc_pipe.cuh: gemm_split), and after EVERY stage the row
+// threads add D0 + D1 to the running gradient on the CUDA cores (round-to-nearest), so that each stage starts from zero.
+// The hardware's truncating accumulate would otherwise shrink the running gradient coherently -- it is shared by every
+// edge of the node, so the bias does not average out: guidance-gradient median error 1.7e-5 with one chained accumulator,
+// 9e-6 with the main / cross split, ~6e-6 = the level of the fp32 node kernel with the per-stage fold.
+// D1 is also the scratch accumulator of the two LayerNorm backwards; the normalised activations
 // of the node tail are parked, as fp16 hi|lo planes, in the very shared-memory bytes that the dc operand planes overwrite.
 // The running gradient `dx` lives in the node-blocked layout (tile_engine.cuh: blk_off) -- it is private to this kernel --
 // so a warp's row threads read and write it as 512 contiguous bytes per instruction.
@@ -139,7 +141,23 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
   const uint32_t lane_base = ps->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t T0 = lane_base + hc, T1 = lane_base + 256 + hc;   // this thread's 128 columns of D0 / D1
   constexpr uint32_t D0 = 0, D1 = 256;
-  const bool have_dx_in = !a.do_final;
+  bool have_dx = !a.do_final;            // false: the running gradient starts from zero (first launch of a backward)
+  // dx += D0 + D1 on the CUDA cores (round-to-nearest), after EVERY stage of the chain: each stage then accumulates from zero,
+  // so the hardware's truncating accumulate (tc_pipe.cuh) acts on that stage's partial sums only instead of on the running
+  // total -- the per-node gradient is shared by every edge of the node, so its bias does not average out.
+  auto fold = [&]() {
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      float v[16], d[16], x[16];
+      tc::tmem_ld16(T0 + c * 16, d);
+      tc::tmem_ld16(T1 + c * 16, x);
+      ld_blocked16(a.dx, n, hc + c * 16, valid && have_dx, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += d[i] + x[i];
+      if (valid) st_blocked16(a.dx, n, hc + c * 16, v);
+    }
+    have_dx = true;
+  };
 
   if (a.do_B) {
     // ---- node_net backward first: it needs both accumulators, and D0 is free until the chain below starts --------------
@@ -229,12 +247,13 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
     uint8_t* q2_lo = q2_hi + tc::ROWS * 128 * 2;
     if (p.role == 0) {
       tc::rows_wait_acc(p);
+      fold();
       stage_cols<C, 32>(q0_hi, q0_lo, row, half * 32, valid ? a.dul + nn * C + half * 32 : nullptr);
       stage_cols<C, 32>(q1_hi, q1_lo, row, half * 32, valid ? a.dur + nn * C + half * 32 : nullptr);
       stage_cols<128, 64>(q2_hi, q2_lo, row, half * 64, valid ? a.dnl + nn * 128 + half * 64 : nullptr);
       tc::rows_publish(p);
     }
-    tc::gemm_split<C, D>(p, q0_hi, q0_lo, TCBB_(BT_EB_NFL), D0, D1, true, true, true, false);
+    tc::gemm_split<C, D>(p, q0_hi, q0_lo, TCBB_(BT_EB_NFL), D0, D1, false, false, true, false);
     tc::gemm_split<C, D>(p, q1_hi, q1_lo, TCBB_(BT_EB_NFR), D0, D1, true, true, false, false);
     tc::gemm_split<128, D>(p, q2_hi, q2_lo, TCBB_(BT_EL_NL), D0, D1, true, true, false, true);
     uint8_t* r0_hi = P;                              // [dnl_R (K = 128) | dgn_L (K = 32) | dgn_R (K = 32)]
@@ -245,16 +264,18 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
     uint8_t* r2_lo = r2_hi + tc::ROWS * 32 * 2;
     if (p.role == 0) {
       tc::rows_wait_acc(p);
+      fold();
       stage_cols<128, 64>(r0_hi, r0_lo, row, half * 64, valid ? a.dnl + (size_t)a.n_nodes * 128 + nn * 128 + half * 64 : nullptr);
       stage_cols<32, 16>(r1_hi, r1_lo, row, half * 16, valid ? a.dgn + nn * 32 + half * 16 : nullptr);
       stage_cols<32, 16>(r2_hi, r2_lo, row, half * 16, valid ? a.dgn + (size_t)a.n_nodes * 32 + nn * 32 + half * 16 : nullptr);
       tc::rows_publish(p);
     }
-    tc::gemm_split<128, D>(p, r0_hi, r0_lo, TCBB_(BT_ER_NL), D0, D1, true, true, true, false);
+    tc::gemm_split<128, D>(p, r0_hi, r0_lo, TCBB_(BT_ER_NL), D0, D1, false, false, true, false);
     tc::gemm_split<32, D>(p, r1_hi, r1_lo, TCBB_(BT_EL_GN), D0, D1, true, true, false, false);
     tc::gemm_split<32, D>(p, r2_hi, r2_lo, TCBB_(BT_ER_GN), D0, D1, true, true, false, true);
     if (p.role == 0) {
       tc::rows_wait_acc(p);
+      fold();
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
         float v[16];
@@ -272,7 +293,7 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       }
       tc::rows_publish(p);
     }
-    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBB_(BT_NB_GX), D0, D1, true, true, true, true);
+    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBB_(BT_NB_GX), D0, D1, false, false, true, true);
   } else {
     // first launch of a backward: dx = ddect W_dec1n  (nothing has reached the node path yet)
     uint8_t* s_hi = P;
@@ -290,17 +311,17 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
     if (p.role == 0) {
       tc::rows_wait_acc(p);                          // D0 = everything linear so far ; the planes are free
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {                  // dx_new = dx_in + (D0 + D1) -> planes ; D0 <- D0 + D1 (D1 is reused below)
+      for (int c = 0; c < 8; ++c) {                  // dx += D0 + D1 ; dx -> planes
         float v[16], d[16], x[16];
         tc::tmem_ld16(T0 + c * 16, d);
         tc::tmem_ld16(T1 + c * 16, x);
-        ld_blocked16(a.dx, n, hc + c * 16, valid && have_dx_in, v);
+        ld_blocked16(a.dx, n, hc + c * 16, valid && have_dx, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { d[i] += x[i]; v[i] += d[i]; }
-        tc::tmem_st16(T0 + c * 16, d);
+        for (int i = 0; i < 16; ++i) v[i] += d[i] + x[i];
+        if (valid) st_blocked16(a.dx, n, hc + c * 16, v);
         store_a16(p_hi, p_lo, row, hc + c * 16, v);
       }
-      tc::tmem_st_wait();
+      have_dx = true;
       tc::rows_publish(p);
       // statistics of u = cen + agg while the GEMM below runs
       RunStat rs = {0.f, 0.f, 0.f};
@@ -372,21 +393,12 @@ __global__ void __launch_bounds__(TC_NB_THREADS, 1) tc_bwd_node_kernel(const __g
       }
       tc::rows_publish(p);
     }
-    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBA_(BT_NB_CEN), D0, D1, true, false, true, true);   // + dc W_cen (d xhat in D1 is dead)
+    tc::gemm_split<D, D>(p, p_hi, p_lo, TCBA_(BT_NB_CEN), D0, D1, false, false, true, true);   // dc W_cen (d xhat in D1 is dead)
   }
 
   if (p.role == 0) {
     tc::rows_wait_acc(p);
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {                    // dx_out = dx_in + D0 (main terms) + D1 (cross terms)
-      float v[16], d[16], x[16];
-      tc::tmem_ld16(T0 + c * 16, d);
-      tc::tmem_ld16(T1 + c * 16, x);
-      ld_blocked16(a.dx, n, hc + c * 16, valid && have_dx_in, v);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += d[i] + x[i];
-      if (valid) st_blocked16(a.dx, n, hc + c * 16, v);
-    }
+    fold();                                          // dx_out
     if (a.do_A) {
       // clear the scatter accumulators that the edge kernels of block i add into (this tile's rows; every read is done)
       asm volatile("bar.sync 1, 256;" ::: "memory");
