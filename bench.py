@@ -430,7 +430,8 @@ def main():
                                                   else "GEOM-Drugs node-count distribution"),
                        "global_batch": total_mols, "n_nodes_rank0": N, "n_edges_rank0": E, "parallelism": f"dp{world}",
                        "l2": "256 MiB flush write between timed iterations", "weights": "random-init (seed 0)",
-                       "cuda_graph": graphed is not None},
+                       "cuda_graph": graphed is not None,
+                       "side_stream_overlap": os.environ.get("MDB_OVERLAP", "1") != "0"},
             "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
         }

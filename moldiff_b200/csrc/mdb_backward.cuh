@@ -893,7 +893,7 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       fa.e = ea.e; fa.dul = dul_cur; fa.dur = dur_cur; fa.dnl = sv.dnl; fa.dgn = sv.dgn;
       fa.de_in = sv.de; fa.dh = sv.dh; fa.dg = sv.dg;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
-      static const bool ffn_bwd2 = []() { const char* e = getenv("MDB_TC_FFN_BWD2"); return e == nullptr || e[0] != '0'; }();
+      const bool ffn_bwd2 = []() { const char* e = getenv("MDB_TC_FFN_BWD2"); return e == nullptr || e[0] != '0'; }();   // (read per call: A/B inside one process)
       if (ffn_bwd2)
         LAUNCH(MDB_K_tc_bondffn_bwd, st,
                (tc_bondffn_bwd2_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN_BWD2, st>>>(fa)));

@@ -23,8 +23,9 @@ WANT = {
     "smsp__inst_executed.sum": "inst_executed",
 }
 CLASS = [("tc_nodeblock_bwd", "tc_nodeblock_bwd"), ("tc_nodeblock_fwd", "tc_nodeblock"), ("tc_bondffn_bwd", "tc_bondffn_bwd"),
-         ("tc_bondffn_fwd", "tc_bondffn"), ("tc_edge_d", "tc_edge_d"), ("tc_node_kernel", "tc_node"),
-         ("transition_step", "transition"), ("bwd_node", "bwd_node"), ("bwd_edge_tail", "bwd_edge_tail")]
+         ("tc_bondffn_fwd", "tc_bondffn"), ("tc_edge_d", "tc_edge_d"), ("tc_node_kernel", "tc_node"), ("tc_bwd_node", "tc_node_bwd"),
+         ("tc_edge_tail_bwd", "tc_edge_tail_bwd"), ("transition_step", "transition"), ("bwd_node", "bwd_node"),
+         ("bwd_edge_tail", "bwd_edge_tail"), ("node_kernel", "node")]
 
 
 def main(out, paths):
