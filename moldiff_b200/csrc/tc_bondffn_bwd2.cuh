@@ -9,14 +9,15 @@
 //   * the sigmoid of the gate is re-evaluated from the parked gate accumulator instead of living in 32 registers;
 //   * the left FFN's d node_linear / d gate-node gradients are reduced over the CSR runs of the tile in shared memory
 //     (one atomic per (node, channel) per tile, as the forward kernels do) instead of same-address REDs;
-//   * 8 KB weight-ring slots (widest N here is 128): the 32 KB saved hold the fp32 run-reduction tile.
+//   * the weight ring carries several K stages per slot (packed slots, tc_pipe.cuh); a 32 KB fp32 tile next to it serves the
+//     run reduction.
 // MDB_TC_FFN_BWD2=0 selects the old kernel (A/B runs).
 //
 // Included by mdb_forward.cu inside its anonymous namespace (after tc_edge_tail_bwd.cuh: tail_tile_off).
 #pragma once
 #include "tc_pipe.cuh"
 
-constexpr uint32_t FB2_SLOT = tc::WStage<128, tc::KB>::STAGE_BYTES;                  // 8 KB
+constexpr uint32_t FB2_SLOT = 2 * tc::WStage<128, tc::KB>::STAGE_BYTES;              // 16 KB: two N = 128 stages, four N = 64, eight N = 32 per slot (tc_pipe.cuh: packed slots)
 constexpr size_t FB2_OFF_A = 2 * (size_t)tc::ROWS * C * 2;                            // after the E planes (32 KB)
 constexpr size_t FB2_OFF_G = FB2_OFF_A + 2 * (size_t)tc::ROWS * 128 * 2;              // after the A planes (64 KB)
 constexpr size_t FB2_OFF_RING = FB2_OFF_G + 2 * (size_t)tc::ROWS * 32 * 2;            // after the gate planes (16 KB)

@@ -87,6 +87,23 @@ __device__ __forceinline__ void stage_load_elect(void* dst_smem, const void* src
       : "memory");
 }
 
+// Building blocks of a slot filled by several bulk copies (second pass of a cross-first GEMM: hi planes only, tc_pipe.cuh)
+__device__ __forceinline__ void expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_elect(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // Two bulk copies (n2 = 0: one) landing on one barrier phase: the second pass of a cross-first GEMM (tc_pipe.cuh) brings the hi
 // planes of two K steps into one ring slot.
 __device__ __forceinline__ void stage_load2_elect(void* dst_smem, const void* src0, const void* src1, uint32_t bytes_each,

@@ -161,27 +161,47 @@ __device__ __forceinline__ int kstep_of(int s) {
 // Which kernels pay for it: the bond predictor's FORWARD kernels (whose saved activations feed the guidance gradient); the
 // denoiser's forward meets its 1e-4 output bar 30 x over in the interleaved order, and the backward kernels measured
 // 2e-6..6e-6 against fp64 in it.  XF is a property of the pipe type, so a kernel picks the order for all its GEMMs.
+// Packed slots.  A weight stage of a narrow GEMM is small (N = 64: 4 KB, N = 32: 2 KB) but used to occupy a whole ring slot: with
+// 3-4 slots only 3-4 K steps were in flight against an L2 round trip of ~800 cycles, i.e. ~270 cycles per K step for 96 cycles
+// of MMA -- the phase table of tc_nodeblock_bwd16 shows 5.4 k cycles for its K = 256, N = 64 GEMMs (1.5 k of MMA), every
+// BondFFN GEMM 2-3 k.  Consecutive K stages are contiguous in the operand image, so ONE bulk copy now brings as many stages as
+// fit a slot (SPS = slot_bytes / STAGE_BYTES) and the issuing warp walks them under one full / empty round trip.  Not for the
+// sliced protocol (its K order is permuted; its stages fill a slot anyway).
 template <int K, int N, int NSLOT, int NPARTS = 0, bool XF = false>
 __device__ __forceinline__ void gemm(PipeT<NSLOT, XF>& p, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_img,
                                      uint32_t d_col, bool accumulate, bool wait_ready, bool signal_done) {
   using WS = WStage<N, KB>;
   constexpr int NS = K / KB;
-  constexpr int NS2 = XF ? (NS + 1) / 2 : 0;     // second pass: two hi planes per ring slot
   static_assert(K % KB == 0, "K must be a multiple of the stage depth");
   static_assert(KB == 16, "one UMMA K step per weight stage");
+  // stages per slot (first pass) / hi planes per slot (second pass of the cross-first order); 1 in the sliced protocol
+  int sps = 1, hps = 1;
+  if constexpr (NPARTS == 0) {
+    sps = (int)(p.slot_bytes / WS::STAGE_BYTES);
+    sps = sps < 1 ? 1 : (sps > NS ? NS : sps);
+    hps = (int)(p.slot_bytes / WS::PLANE_BYTES);
+    hps = hps < 1 ? 1 : (hps > NS ? NS : hps);
+  } else {
+    hps = (int)(p.slot_bytes / WS::PLANE_BYTES) >= 2 ? 2 : 1;
+  }
   if (p.role == 1) {
-    for (int s = 0; s < NS; ++s, ++p.it) {
+    for (int s0 = 0; s0 < NS; s0 += sps, ++p.it) {
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
+      const int n = (NS - s0) < sps ? (NS - s0) : sps;
       mbar_wait(&p.s->empty[slot], ph ^ 1);
-      stage_load_elect(p.stages + slot * p.slot_bytes, w_img + (size_t)kstep_of<NS, NPARTS>(s) * WS::STAGE_BYTES,
-                       WS::STAGE_BYTES, &p.s->full[slot]);
+      stage_load_elect(p.stages + slot * p.slot_bytes, w_img + (size_t)kstep_of<NS, NPARTS>(s0) * WS::STAGE_BYTES,
+                       (uint32_t)n * WS::STAGE_BYTES, &p.s->full[slot]);
     }
-    for (int j = 0; j < NS2; ++j, ++p.it) {
-      const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
-      mbar_wait(&p.s->empty[slot], ph ^ 1);
-      const uint8_t* h0 = w_img + (size_t)(2 * j) * WS::STAGE_BYTES;
-      stage_load2_elect(p.stages + slot * p.slot_bytes, h0, h0 + WS::STAGE_BYTES, WS::PLANE_BYTES,
-                        (2 * j + 1 < NS) ? 1u : 0u, &p.s->full[slot]);
+    if constexpr (XF) {
+      for (int s0 = 0; s0 < NS; s0 += hps, ++p.it) {
+        const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
+        const int n = (NS - s0) < hps ? (NS - s0) : hps;
+        mbar_wait(&p.s->empty[slot], ph ^ 1);
+        expect_tx_elect(&p.s->full[slot], (uint32_t)n * WS::PLANE_BYTES);
+        for (int j = 0; j < n; ++j)       // the hi plane is the first half of every stage image
+          bulk_g2s_elect(p.stages + slot * p.slot_bytes + (size_t)j * WS::PLANE_BYTES, w_img + (size_t)(s0 + j) * WS::STAGE_BYTES,
+                         WS::PLANE_BYTES, &p.s->full[slot]);
+      }
     }
   } else if (p.role == 2) {
     const uint32_t ready_parity = p.n_ready & 1;
@@ -204,40 +224,45 @@ __device__ __forceinline__ void gemm(PipeT<NSLOT, XF>& p, const uint8_t* a_hi, c
     const uint32_t slot_units = p.slot_bytes >> 4;
     const bool leader = (threadIdx.x & 31) == 0;      // all lanes walk the loop and wait; one elected lane issues
 #pragma unroll 1                                      // rolled: a handful of live registers (the warpgroup keeps 32)
-    for (int s = 0; s < NS; ++s, ++p.it) {
+    for (int s0 = 0; s0 < NS; s0 += sps, ++p.it) {
       if constexpr (NPARTS != 0) {
-        if (wait_ready && s % (NS / NGRP) == 0) {
-          mbar_wait(&p.s->a_ready[s / (NS / NGRP)], ready_parity);
+        if (wait_ready && s0 % (NS / NGRP) == 0) {
+          mbar_wait(&p.s->a_ready[s0 / (NS / NGRP)], ready_parity);
           fence_after_sync();
-          if (p.dbg && leader) p.dbg[16 + s / (NS / NGRP)] = clock64();
+          if (p.dbg && leader) p.dbg[16 + s0 / (NS / NGRP)] = clock64();
         }
       }
       const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
+      const int n = (NS - s0) < sps ? (NS - s0) : sps;
       mbar_wait(&p.s->full[slot], ph);
       fence_after_sync();
-      const uint32_t ks = (uint32_t)kstep_of<NS, NPARTS>(s);
-      const uint64_t da_hi = da_hi0 + ks * 16u, da_lo = da_lo0 + ks * 16u;   // + ks * 256 bytes
-      const uint64_t db_hi = db0 + slot * slot_units, db_lo = db_hi + (WS::PLANE_BYTES >> 4);
-      if constexpr (XF) {
-        mma_f16_ss_elect<false>(d_tmem, da_lo, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
-        mma_f16_ss_elect<true>(d_tmem, da_hi, db_lo, idesc);
-      } else {
-        mma_f16_ss_elect<false>(d_tmem, da_hi, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
-        mma_f16_ss_elect<true>(d_tmem, da_lo, db_hi, idesc);
-        mma_f16_ss_elect<true>(d_tmem, da_hi, db_lo, idesc);
+#pragma unroll 1
+      for (int j = 0; j < n; ++j) {
+        const int s = s0 + j;
+        const uint32_t ks = (uint32_t)kstep_of<NS, NPARTS>(s);
+        const uint64_t da_hi = da_hi0 + ks * 16u, da_lo = da_lo0 + ks * 16u;   // + ks * 256 bytes
+        const uint64_t db_hi = db0 + slot * slot_units + (uint32_t)j * (WS::STAGE_BYTES >> 4), db_lo = db_hi + (WS::PLANE_BYTES >> 4);
+        if constexpr (XF) {
+          mma_f16_ss_elect<false>(d_tmem, da_lo, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
+          mma_f16_ss_elect<true>(d_tmem, da_hi, db_lo, idesc);
+        } else {
+          mma_f16_ss_elect<false>(d_tmem, da_hi, db_hi, idesc, (accumulate || s > 0) ? 1u : 0u);
+          mma_f16_ss_elect<true>(d_tmem, da_lo, db_hi, idesc);
+          mma_f16_ss_elect<true>(d_tmem, da_hi, db_lo, idesc);
+        }
       }
       mma_commit_elect(&p.s->empty[slot]);
     }
     if constexpr (XF) {
 #pragma unroll 1
-      for (int j = 0; j < NS2; ++j, ++p.it) {          // second pass: hi * hi, two K steps per ring slot
+      for (int s0 = 0; s0 < NS; s0 += hps, ++p.it) {   // second pass: hi * hi, `hps` K steps per ring slot
         const uint32_t slot = p.it % NSLOT, ph = (p.it / NSLOT) & 1;
+        const int n = (NS - s0) < hps ? (NS - s0) : hps;
         mbar_wait(&p.s->full[slot], ph);
         fence_after_sync();
-        const uint64_t da = da_hi0 + (uint32_t)(2 * j) * 16u;
-        const uint64_t db = db0 + slot * slot_units;
-        mma_f16_ss_elect<true>(d_tmem, da, db, idesc);
-        if (2 * j + 1 < NS) mma_f16_ss_elect<true>(d_tmem, da + 16u, db + (WS::PLANE_BYTES >> 4), idesc);
+#pragma unroll 1
+        for (int j = 0; j < n; ++j)
+          mma_f16_ss_elect<true>(d_tmem, da_hi0 + (uint32_t)(s0 + j) * 16u, db0 + slot * slot_units + (uint32_t)j * (WS::PLANE_BYTES >> 4), idesc);
         mma_commit_elect(&p.s->empty[slot]);
       }
     }
