@@ -951,6 +951,13 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   LAUNCH(MDB_K_node_init, st,
          (node_init_kernel<<<N, D, 0, st>>>(net->kind, N, net->num_node_types, net->time_dim, net->num_timesteps,
                                             net->blob, head, in.h_node, in.batch_node, in.t, in.node_time, tb.x, tb.tn)));
+  // pre(0) -- the hoisted tables of block 0, a 50...99-CTA node kernel that needs node_init only -- runs on the side stream
+  // beside the edge initialisation (an E-sized elementwise kernel) and the two small memory operations
+  const bool fork0 = overlap && side != nullptr && E > 0;
+  if (fork0) {
+    CUDA_TRY(cudaEventRecord(side->fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
+  }
   if (E > 0) {
     LAUNCH(MDB_K_edge_init, st,
            (edge_init_kernel<<<(E + 3) / 4, 256, 0, st>>>(net->kind, E, net->num_node_types, net->num_edge_types,
@@ -972,8 +979,12 @@ int run_forward(const mdb_net_desc* net, const mdb_plan* plan, const FwdIn& in, 
   na.do_mid = 0; na.do_pre = 1; na.do_dec = 0; na.pos_cur = pos_cur; na.pos_nxt = pos_nxt;
   na.sl_next = sl_of(0); na.fl_next = fl_of(0); na.fr_next = fr_of(0);
   na.x_save = in.save ? sv.x : nullptr; na.agg_save = nullptr;
-  rc = launch_node(net, na, -1, 0, node_tiles, st);
+  rc = launch_node(net, na, -1, 0, node_tiles, fork0 ? side->s : st);
   if (rc) return rc;
+  if (fork0) {
+    CUDA_TRY(cudaEventRecord(side->join, side->s));
+    CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+  }
 
   EdgeArgs ea;
   memset(&ea, 0, sizeof(ea));
