@@ -6,11 +6,15 @@ NodeEdgeNet denoiser) + posterior sampling + (guided workloads) BondPredictor fo
 Per-step cost does not depend on t, so
         molecules/sec @ 1000 steps = n_molecules / (1000 * seconds_per_step).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload guided|unguided] [--batch B]
+The step is replayed as ONE CUDA graph (MolDiff.graphed_step -- what MolDiff.sample does by default; --no-graph launches kernel by
+kernel); tools/full_sample_run.py times a complete 1000-step MolDiff.sample next to this per-step figure.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload guided|unguided|train_fwd] [--batch B] [--simple] [--no-graph]
   python bench.py --impl reference ...      # the CPU oracle port (reference's own op sequence) on host cores
 
 N > 1: launched by torch.distributed.run, one rank per GPU; molecules are sharded (weak scaling, B per
-GPU fixed), no data-path collective; one NCCL gather of the final predictions after the timed region.
+GPU fixed; --strong --batch 2048: ONE batch split by balancing sum n^2), no data-path collective; one NCCL gather of
+the final predictions after the timed region.
 """
 import argparse
 import json

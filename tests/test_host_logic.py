@@ -295,6 +295,27 @@ def test_sharding_and_gather_gloo_world2():
     assert root[1] > other[0] and root[2] > other[1]         # rank 0's + rank 1's atoms / half-edges
 
 
+def test_balanced_shards_strong_scaling():
+    """Strong-scaling split of ONE batch (bench.py --strong; config 4 = 2 048 molecules over 8 GPUs): every molecule lands on
+    exactly one rank, batch order is kept inside a shard, and sum n^2 -- the per-edge work -- is balanced to ~1 %, which a split
+    by molecule COUNT is not."""
+    import numpy as np
+    from moldiff_b200.sharding import balanced_shards
+    rng = np.random.RandomState(7)
+    sizes = rng.randint(8, 60, size=2048)
+    for world in (1, 2, 4, 8):
+        shards = balanced_shards(sizes, world)
+        assert len(shards) == world
+        allm = np.concatenate(shards)
+        assert sorted(allm.tolist()) == list(range(2048))
+        assert all((np.diff(s) > 0).all() for s in shards)
+        load = np.array([(sizes[s].astype(np.int64) ** 2).sum() for s in shards])
+        assert load.max() / load.mean() < 1.01, load
+    by_count = np.array([(sizes[i::8].astype(np.int64) ** 2).sum() for i in range(8)])
+    assert balanced_shards(sizes, 8) and by_count.max() / by_count.mean() > 1.01
+    assert [len(s) for s in balanced_shards([5, 5, 5], 8)].count(0) == 5          # more ranks than molecules: empty shards
+
+
 def test_new_ops_refuse_cpu_tensors():
     """No CPU / eager fallback behind the round-1 additions either: the fused transition step, the batch decode and the edge
     builders raise on CPU tensors instead of computing something (the unfused PyTorch transition operators remain the
