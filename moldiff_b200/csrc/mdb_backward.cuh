@@ -717,6 +717,7 @@ int ensure_bwd_attrs() {
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD));
   CUDA_TRY(cudaFuncSetAttribute(tc_edge_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_EDGE_TAIL_BWD));
   CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD2));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bondffn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_FFN_BWD3));
   CUDA_TRY(cudaFuncSetAttribute(tc_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TC_BWD_NODE));
   if (dev >= 0 && dev < 64) done[dev] = true;
   return MDB_OK;
@@ -894,7 +895,11 @@ int run_bondpred_backward(const mdb_net_desc* net, const mdb_plan* plan, const f
       fa.de_in = sv.de; fa.dh = sv.dh; fa.dg = sv.dg;
       fill_ffn_vecs(fa.v, net->blob_host, ea.off, head);
       const bool ffn_bwd2 = []() { const char* e = getenv("MDB_TC_FFN_BWD2"); return e == nullptr || e[0] != '0'; }();   // (read per call: A/B inside one process)
-      if (ffn_bwd2)
+      const bool ffn_bwd3 = []() { const char* e = getenv("MDB_TC_FFN_BWD3"); return e == nullptr || e[0] != '0'; }();
+      if (ffn_bwd3)             // 16 row warps (tc_bondffn_bwd3.cuh); MDB_TC_FFN_BWD3=0 -> the 8-row-warp kernels below
+        LAUNCH(MDB_K_tc_bondffn_bwd, st,
+               (tc_bondffn_bwd3_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, NB16_THREADS, SMEM_TC_FFN_BWD3, st>>>(fa)));
+      else if (ffn_bwd2)
         LAUNCH(MDB_K_tc_bondffn_bwd, st,
                (tc_bondffn_bwd2_kernel<<<(E + tc::ROWS - 1) / tc::ROWS, TC_NB_THREADS, SMEM_TC_FFN_BWD2, st>>>(fa)));
       else

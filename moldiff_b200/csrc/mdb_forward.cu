@@ -683,6 +683,7 @@ __global__ void edge_unsort_kernel(int n_edges, const int* __restrict__ perm, co
 #include "tc_node.cuh"
 #include "tc_edge_tail_bwd.cuh"
 #include "tc_bondffn_bwd2.cuh"
+#include "tc_bondffn_bwd3.cuh"
 #include "tc_bwd_node.cuh"
 
 // ------------------------------------------------------------------------------------------------
