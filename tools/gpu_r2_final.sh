@@ -24,7 +24,7 @@ timeout 300 python tools/tc_phase_times_ffn.py > $O/phase_times_ffn2.txt 2>&1
 export MDB_OVERLAP=0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches.csv \
    python bench.py --workload guided --no-graph --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_launch.log 2>&1
-for k in tc_nodeblock_fwd16 tc_nodeblock_bwd16 tc_bondffn_fwd2 tc_bondffn_bwd2 tc_edge_d tc_node_kernel tc_bwd_node tc_edge_tail_bwd ^node_kernel transition_step; do
+for k in tc_nodeblock_fwd16 tc_nodeblock_bwd16 tc_bondffn_fwd2 tc_bondffn_bwd3 tc_edge_d tc_node_kernel tc_bwd_node tc_edge_tail_bwd ^node_kernel transition_step; do
   n=${k#^}
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 1 -c 1 -f -o $O/full_$n \
      python bench.py --workload guided --no-graph --steps 1 --warmup 0 --no-cpu-baseline > $O/ncu_$n.log 2>&1
